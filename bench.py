@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the fused CollectiveCrossing step kernel (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] geometry and policy — the README 12x8 grid
+with 5 boarding + 3 exiting agents, DefaultReward, IndividualAtDestination, MaxSteps 100, greedy
+baseline policy evaluated inside the step kernel, auto-reset — at 1,048,576 envs per GPU (the
+north_star's roofline size; the per-step working set of 1.4 GB is far larger than L2, so no
+flush is needed between iterations).  A "step" is one fused kernel launch over all envs.
+Metric: agent-steps/s = env-steps x 8 agent slots, whole job.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "agent_steps_per_sec"
+UNIT = "agent-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--obs-dtype", default="float32", choices=["float32", "int8", "none"])
+    ap.add_argument("--policy", default="greedy", choices=["greedy", "waiting", "random"])
+    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def workload_config():
+    from cases import readme_config
+
+    return readme_config()
+
+
+def config_dict(args, n_total):
+    return {
+        "workload": f"BASELINE configs[1]: README 12x8 grid, door 5-7, 5 boarding + 3 exiting agents, DefaultReward, "
+                    f"IndividualAtDestination, MaxSteps 100, {args.policy} baseline policy in-kernel, auto-reset; "
+                    f"{args.envs} envs per GPU",
+        "envs_total": n_total, "envs_per_gpu": args.envs, "agents_per_env": 8, "obs_dtype": args.obs_dtype,
+        "policy": args.policy, "l2_policy": "inputs larger than L2 (no flush)" if args.envs >= 1 << 19 else "working set may fit L2",
+        "parallelism": "independent env shards, one process per GPU, no data-path collective",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.split(",") for r in Path(self.tmp.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.tmp.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any("Active" == r[5 + k].strip() for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_c_oracle(args, seconds):
+    """The C oracle (OpenMP, all host threads) on a bounded sample of the same workload."""
+    import oracle
+    from collectivecrossing_b200 import _abi
+    from collectivecrossing_b200.lowering import lower_config
+
+    cores = os.cpu_count() or 1
+    n = 65536
+    code = {"float32": _abi.OBS_FP32, "int8": _abi.OBS_INT8, "none": _abi.OBS_NONE}[args.obs_dtype]
+    orc = oracle.OracleEnvs(lower_config(workload_config()), n, seed=1)
+    orc.reset()
+    for _ in range(2):
+        orc.step(policy=args.policy, auto_reset=True, obs_dtype=code)
+    t0 = time.perf_counter()
+    steps = 0
+    while time.perf_counter() - t0 < seconds and steps < 400:
+        orc.step(policy=args.policy, auto_reset=True, obs_dtype=code)
+        steps += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * 8 * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"C oracle (oracle/cc_oracle.c, OpenMP x{cores}): {n} envs x {steps} steps of the same workload in {dt:.1f} s"}
+
+
+def _py_worker(job):
+    policy, seconds, seed = job
+    from oracle.pyport import PyEnv
+
+    env = PyEnv(workload_config())
+    env.reset(seed=seed)
+    for _ in range(50):
+        env.step(env.policy_actions(policy) if policy != "random" else {})
+    t0 = time.perf_counter()
+    steps = 0
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(100):
+            acts = env.policy_actions(policy) if policy != "random" else {i: int(rng.integers(0, 5)) for i in env.agents}
+            _, _, term, trunc, _ = env.step(acts)
+            steps += 1
+            if term["__all__"] or trunc["__all__"]:
+                env.reset()
+    return steps, time.perf_counter() - t0
+
+
+def cpu_python_port(args, seconds):
+    """The reference's own shape of computation: a pure-Python env + policy loop, one independent
+    env per host core (multiprocessing), reset() on episode end."""
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_py_worker, [(args.policy, seconds, 1000 + k) for k in range(cores)])
+    rate = sum(s / dt for s, dt in res) * 8
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"pure-Python port of the reference loop (oracle/pyport.py), {cores} processes x 1 env, "
+                      f"{sum(s for s, _ in res)} env-steps in {seconds:.0f} s each, {args.policy} policy + step + reset on done"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step_seconds = max(1.0, min(6.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    info = None
+    for k in range(args.warmup + args.steps):
+        info = cpu_python_port(args, per_step_seconds)
+        if k >= args.warmup:
+            vals.append(info["value"])
+        if k >= args.warmup and len(vals) >= 3 and (k + 1) * per_step_seconds > 150:
+            break
+    value = sum(vals) / len(vals)
+    info["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": per_step_seconds * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "python int / float64", "data": "synthetic", "config": config_dict(args, args.envs * args.gpus),
+        "cpu_baseline": info, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def time_steps(env, torch, dist, args, steps, policy, world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        env.step(policy=policy)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=env.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from collectivecrossing_b200 import BatchedCollectiveCrossing
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    cfg = workload_config()
+    n = args.envs
+    A = 8
+    env = BatchedCollectiveCrossing(cfg, n, dev, seed=2026, global_env_offset=rank * n, obs_dtype=args.obs_dtype, auto_reset=True)
+    env.reset()
+    for _ in range(args.warmup):
+        env.step(policy=args.policy)
+    torch.cuda.synchronize()
+    env.reset_stats()
+    launches0 = env.launch_count
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = time_steps(env, torch, dist, args, args.steps, args.policy, world)
+    clocks = sampler.stop() if sampler else None
+    launches = env.launch_count - launches0
+    env.check_error()
+
+    # episode statistics: the one collective of the job (NCCL all-reduce of 8 scalars per chunk)
+    st = env.stats()
+    if world > 1:
+        keys = list(st)
+        t = torch.tensor([float(st[k]) for k in keys], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        st = dict(zip(keys, t.tolist()))
+
+    agent_steps = float(n) * A * args.steps * world
+    value = agent_steps / (ms * 1e-3)
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    bytes_per_launch = env.algorithmic_bytes_per_env_step() * n
+    achieved = bytes_per_launch / (ms / args.steps * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(f"{args.obs_dtype}_{args.policy}_{n}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernel": "ccb::cc_kernel<8,1,%s,step>" % {"float32": 4, "int8": 1, "none": 0}[args.obs_dtype],
+                "algorithmic_bytes_per_env_step": env.algorithmic_bytes_per_env_step(),
+                "formula": "12A+17+s_obs*A*(6+4A), A=8 (SURVEY.md 8d)"}
+
+    # ---- e2e: host buffers through the C ABI (cc_policy_actions -> D2H -> cc_step_host) ----------
+    host = env.make_host_buffers(pinned=True)
+    dev_actions = torch.zeros((n, A), dtype=torch.int8, device=dev)
+
+    def e2e_step():
+        env.policy_actions(args.policy, out=dev_actions)
+        host["actions"].copy_(dev_actions, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        env.step_host(host)
+
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    wall = (time.perf_counter() - t0) * 1e3
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), wall)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    obs_bytes = 0 if host["obs"] is None else host["obs"].numel() * host["obs"].element_size()
+    d2h = n * A + obs_bytes + host["reward"].numel() * 4 + 2 * n * A + n  # policy actions, obs, reward, flags+actions_out, env_flags
+    e2e = {"value": float(n) * A * args.e2e_steps * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * A,
+           "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+           "path": "cc_policy_actions -> D2H actions (pinned) -> cc_step_host(H2D actions, fused step kernel, D2H obs/reward/flags)"}
+    launches_e2e = env.launch_count - launches0 - launches
+
+    extras = {}
+    if not args.no_extras and world == 1:
+        del host
+        extras = secondary(args, torch, dist, cfg)
+
+    if rank == 0:
+        cpu = cpu_c_oracle(args, args.cpu_seconds) if world == 1 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 lattice state, float64->float32 rewards", "data": "synthetic",
+            "config": config_dict(args, n * world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "gpu_launches_e2e": launches_e2e, "roofline": roofline, "cpu_baseline": cpu,
+            "episode_stats": st, "extras": extras,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def secondary(args, torch, dist, cfg):
+    """Secondary single-GPU measurements (reported under "extras", never as `value`)."""
+    from collectivecrossing_b200 import BatchedCollectiveCrossing
+
+    out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for tag, n, obs, pol in (("cfg2_65536_envs_fp32_greedy", 65536, "float32", "greedy"), ("1M_envs_int8_greedy", 1 << 20, "int8", "greedy"),
+                             ("1M_envs_noobs_greedy", 1 << 20, "none", "greedy"), ("1M_envs_fp32_waiting", 1 << 20, "float32", "waiting"),
+                             ("1M_envs_fp32_random", 1 << 20, "float32", "random")):
+        env = BatchedCollectiveCrossing(cfg, n, dev, seed=1, obs_dtype=obs, auto_reset=True)
+        env.reset()
+        for _ in range(10):
+            env.step(policy=pol)
+        ms = time_steps(env, torch, dist, args, 50, pol, 1)
+        b = env.algorithmic_bytes_per_env_step() * n
+        out[tag] = {"agent_steps_per_sec": n * 8 * 50 / (ms * 1e-3), "ms_per_step": ms / 50, "algorithmic_GBps": b / (ms / 50 * 1e-3) / 1e9}
+        env.close()
+        del env
+        torch.cuda.empty_cache()
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

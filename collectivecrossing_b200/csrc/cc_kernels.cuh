@@ -1,0 +1,762 @@
+// cc_kernels.cuh — sm_100a kernels of the batched CollectiveCrossing step / reset path.
+//
+// Mapping: a TILE of LPE lanes (4, 8, 16 or 32) owns one env; a lane owns APL
+// agents (agent a = lane_in_tile + slot*LPE).  A warp therefore processes EPW = 32/LPE
+// consecutive envs per iteration of a persistent grid-stride loop, and every per-agent array
+// ([N][A], env-major) is read / written as one contiguous run of bytes per warp.
+//
+// The semantics follow the reference function by function (file:line cited at each device
+// function; paths relative to /root/reference/src/collectivecrossing/).  oracle/cc_oracle.c is
+// the CPU restatement the tests diff this file against.
+#pragma once
+#include <cuda_runtime.h>
+#include <type_traits>
+#include <stdint.h>
+
+#include "../../include/ccb200.h"
+
+namespace ccb {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kResetAttemptCap = 4096;   // same cap as the oracle
+
+enum Mode { kModeStep = 0, kModeReset = 1, kModePolicy = 2, kModeObserve = 3 };
+enum StatSlot { kStEnvSteps = 0, kStEpisodes, kStTermAll, kStTruncAll, kStArrivals, kStEpLen, kStEpRet, kStRewardSum, kStCount };
+enum ErrBit { kErrInvalidAction = 1, kErrResetStuck = 2 };
+
+struct KParams {
+    // lowered config (cc_config) + derived
+    int W, H, D, TL, TR, DL, DR, DC, YB, YE, B, A;
+    int max_steps, reward_kind, terminated_kind;
+    double rp[4];
+    // shard
+    long long n_envs;
+    unsigned long long genv_offset, seed;
+    unsigned t;
+    // persistent state
+    int8_t *x, *y;
+    uint8_t *flags;
+    int32_t *step;
+    float *ep_ret;
+    // step io
+    const int8_t *actions, *order;
+    const uint8_t *mask;  // reset mode
+    int8_t *actions_out;
+    void *obs, *reward;
+    uint8_t *agent_flags, *agent_info, *env_flags;
+    int policy, auto_reset, reward_f64;
+    // bookkeeping
+    unsigned long long *stats;  // kStCount 8-byte slots (int64 / double bit patterns)
+    int *err;
+    // shared-memory layout (bytes from the dynamic smem base)
+    int R;               // pairs per observation row = 3 + 2A
+    int pairs_per_env;   // A * R
+    int lut_entries;     // EPW * A * R
+    int stage_pairs;     // 3 + EPW * 2A (per warp)
+    int bitmap_words;    // per env: ceil((W+1)(H+1)/32); 0 when no on-device policy can run
+    int off_stage, off_bitmap, off_red;
+    long long n_groups;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based; auto-reset placement and random actions).  Same constants and
+// counter layout as oracle/cc_oracle.c:orc_draw.
+// ---------------------------------------------------------------------------------------------
+struct U4 { unsigned v0, v1, v2, v3; };
+
+__device__ __forceinline__ U4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        unsigned h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        unsigned n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return U4{c0, c1, c2, c3};
+}
+enum { kStreamReset = 0, kStreamAction = 1 };
+__device__ __forceinline__ U4 draw(const KParams &p, unsigned long long genv, unsigned stream, unsigned idx) {
+    return philox4x32_10((unsigned)genv, (unsigned)(genv >> 32), p.t, (stream << 24) | (idx & 0xFFFFFFu),
+                         (unsigned)p.seed, (unsigned)(p.seed >> 32));
+}
+__device__ __forceinline__ int bounded(unsigned r, int n) { return (int)__umulhi(r, (unsigned)n); }
+
+// ---------------------------------------------------------------------------------------------
+// geometry predicates
+// ---------------------------------------------------------------------------------------------
+// collectivecrossing.py:509-534 _is_valid_position.  (:565-588 _would_hit_tram_wall rejects a
+// subset of what this rejects, so _is_move_valid's geometric part is exactly this test.)
+__device__ __forceinline__ bool valid_position(const KParams &p, int x, int y) {
+    bool ok = (unsigned)x <= (unsigned)p.W && (unsigned)y <= (unsigned)p.H;
+    if (y == p.D) ok = ok && (p.DL < x) && (x < p.DR);
+    if (y >= p.D) ok = ok && (p.TL < x) && (x < p.TR);
+    return ok;
+}
+// collectivecrossing.py:551-554 is_in_tram_area (inclusive)
+__device__ __forceinline__ bool in_tram_area(const KParams &p, int x, int y) { return y >= p.D && p.TL <= x && x <= p.TR; }
+// collectivecrossing.py:556-563 is_at_tram_door
+__device__ __forceinline__ bool at_tram_door(const KParams &p, int x, int y) { return y == p.D && (x == p.DL - 1 || x == p.DR + 1); }
+// actions.py:18-24 ACTION_TO_DIRECTION
+__device__ __forceinline__ int act_dx(int a) { return (a == CC_ACT_RIGHT) - (a == CC_ACT_LEFT); }
+__device__ __forceinline__ int act_dy(int a) { return (a == CC_ACT_UP) - (a == CC_ACT_DOWN); }
+
+__device__ __forceinline__ unsigned pack_pos(int x, int y) { return ((unsigned)(x & 0xff) << 8) | (unsigned)(y & 0xff); }
+__device__ __forceinline__ int pos_x(unsigned q) { return (int)(int8_t)(q >> 8); }
+__device__ __forceinline__ int pos_y(unsigned q) { return (int)(int8_t)(q & 0xff); }
+
+// the geometric half of collectivecrossing.py:378-408 _move_agent: bit31 = "wants to move and the
+// target passes _is_valid_position", low 16 bits = packed target
+__device__ __forceinline__ unsigned move_request(const KParams &p, unsigned pos, int action, bool active) {
+    int nx = pos_x(pos) + act_dx(action), ny = pos_y(pos) + act_dy(action);
+    bool go = active && (unsigned)action < 4u && valid_position(p, nx, ny);
+    return (go ? 0x80000000u : 0u) | pack_pos(nx, ny);
+}
+
+template <int APL>
+__device__ __forceinline__ unsigned pick(const unsigned (&v)[APL], int slot) {
+    unsigned r = v[0];
+#pragma unroll
+    for (int k = 1; k < APL; ++k) r = (slot == k) ? v[k] : r;
+    return r;
+}
+template <int APL>
+__device__ __forceinline__ int picki(const int (&v)[APL], int slot) {
+    int r = v[0];
+#pragma unroll
+    for (int k = 1; k < APL; ++k) r = (slot == k) ? v[k] : r;
+    return r;
+}
+
+template <typename T> struct PairOf;
+template <> struct PairOf<float> { using type = float2; };
+template <> struct PairOf<int8_t> { using type = char2; };
+template <typename T> __device__ __forceinline__ typename PairOf<T>::type mk_pair(int a, int b);
+template <> __device__ __forceinline__ float2 mk_pair<float>(int a, int b) { return make_float2((float)a, (float)b); }
+template <> __device__ __forceinline__ char2 mk_pair<int8_t>(int a, int b) { return make_char2((signed char)a, (signed char)b); }
+
+// ---------------------------------------------------------------------------------------------
+// per-warp context
+// ---------------------------------------------------------------------------------------------
+template <int LPE, int APL>
+struct Tile {
+    static constexpr int EPW = 32 / LPE;
+    static constexpr unsigned MASK = (LPE == 32) ? 0xffffffffu : ((1u << (LPE & 31)) - 1u);
+    static constexpr int LOG = (LPE == 4) ? 2 : (LPE == 8) ? 3 : (LPE == 16) ? 4 : 5;
+    int lane, li, tile, tshift;
+    __device__ __forceinline__ Tile() {
+        lane = threadIdx.x & 31;
+        li = lane & (LPE - 1);
+        tile = lane >> LOG;
+        tshift = tile * LPE;
+    }
+    __device__ __forceinline__ unsigned tballot(bool pred) const { return (__ballot_sync(kFull, pred) >> tshift) & MASK; }
+    __device__ __forceinline__ unsigned tshfl(unsigned v, int src_in_tile) const { return __shfl_sync(kFull, v, src_in_tile, LPE); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// LUT: output pair index within the warp's chunk -> pair index in the warp's stage.
+// Row i of an env is  [P_i, K1, K2, S_0a, S_0b, S_1a, S_1b, ...] with S_ia,S_ib replaced by M
+// (observations.py:62-94), in pair units: P_i=(x_i,y_i) K1=(DC,D) K2=(DL,DR) S_ja=(x_j,y_j)
+// S_jb=(type_j,active_j) M=(-1,-1).  Stage: [K1, K2, M, then per tile 2A pairs S_*].
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void build_lut(const KParams &p, uint16_t *lut) {
+    const int A = p.A, R = p.R, ppe = p.pairs_per_env;
+    for (int P = threadIdx.x; P < p.lut_entries; P += blockDim.x) {
+        int tile = P / ppe, q0 = P - tile * ppe;
+        int i = q0 / R, q = q0 - i * R;
+        int base = 3 + tile * 2 * A;
+        int v;
+        if (q == 0) v = base + 2 * i;
+        else if (q == 1) v = 0;
+        else if (q == 2) v = 1;
+        else { int j = (q - 3) >> 1, h = (q - 3) & 1; v = (j == i) ? 2 : base + 2 * j + h; }
+        lut[P] = (uint16_t)v;
+    }
+}
+
+// Expand the staged table into observation rows: `count` pairs starting at global pair index
+// `gp0` of the obs tensor, written as 16-byte vectors wherever a whole vector lies inside the
+// range (always, except at the two ends of an odd-sized / unaligned chunk).
+template <typename T>
+__device__ __forceinline__ void emit_obs(T *obs, long long gp0, int count, const uint16_t *lut,
+                                         const typename PairOf<T>::type *stage, int lane) {
+    using P2 = typename PairOf<T>::type;
+    constexpr int PPV = 16 / (int)sizeof(P2);  // pairs per 16-byte vector: 2 (fp32) or 8 (int8)
+    P2 *out = reinterpret_cast<P2 *>(obs);
+    const long long v_first = gp0 / PPV, v_last = (gp0 + count - 1) / PPV;
+    for (long long v = v_first + lane; v <= v_last; v += 32) {
+        const int p0 = (int)(v * PPV - gp0);  // chunk-local index of the vector's first pair
+        if (p0 >= 0 && p0 + PPV <= count) {
+            union { uint4 u; P2 e[PPV]; } pk;
+#pragma unroll
+            for (int e = 0; e < PPV; ++e) pk.e[e] = stage[lut[p0 + e]];
+            __stcs(reinterpret_cast<uint4 *>(out + v * PPV), pk.u);
+        } else {
+#pragma unroll
+            for (int e = 0; e < PPV; ++e)
+                if (p0 + e >= 0 && p0 + e < count) out[v * PPV + e] = stage[lut[p0 + e]];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------------
+template <int LPE, int APL, int OBS, int MODE>
+__global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KParams p) {
+    using TL_ = Tile<LPE, APL>;
+    using OT = typename std::conditional<OBS == CC_OBS_FP32, float, int8_t>::type;
+    using P2 = typename PairOf<OT>::type;
+    constexpr int EPW = TL_::EPW;
+    extern __shared__ __align__(16) unsigned char smem[];
+
+    const TL_ T;
+    const int warp = threadIdx.x >> 5;
+    const int A = p.A;
+    uint16_t *lut = reinterpret_cast<uint16_t *>(smem);
+    P2 *stage = reinterpret_cast<P2 *>(smem + p.off_stage) + (size_t)warp * p.stage_pairs;
+    unsigned *bitmap = reinterpret_cast<unsigned *>(smem + p.off_bitmap) + ((size_t)warp * EPW + T.tile) * p.bitmap_words;
+
+    if (OBS != CC_OBS_NONE) {
+        build_lut(p, lut);
+        if (T.lane == 0) { stage[0] = mk_pair<OT>(p.DC, p.D); stage[1] = mk_pair<OT>(p.DL, p.DR); stage[2] = mk_pair<OT>(-1, -1); }
+        __syncthreads();
+    }
+
+    // per-thread statistics (only tile leaders contribute)
+    long long st_steps = 0, st_episodes = 0, st_term = 0, st_trunc = 0, st_arrivals = 0, st_eplen = 0;
+    double st_epret = 0.0, st_rsum = 0.0;
+    int errbits = 0;
+
+    int aidx[APL];
+    bool avalid[APL];
+#pragma unroll
+    for (int k = 0; k < APL; ++k) { aidx[k] = T.li + k * LPE; avalid[k] = aidx[k] < A; }
+
+    const long long total_warps = (long long)gridDim.x * kWarpsPerCta;
+    for (long long g = (long long)blockIdx.x * kWarpsPerCta + warp; g < p.n_groups; g += total_warps) {
+        const long long n = g * EPW + T.tile;
+        const bool env_ok = n < p.n_envs;
+        const unsigned long long genv = p.genv_offset + (unsigned long long)n;
+        const long long row = n * A;
+
+        // ---- load the env's record (one contiguous run of bytes per array per warp) ----------
+        unsigned pos[APL];
+        unsigned fl[APL];
+        int action[APL];
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+            pos[k] = 0; fl[k] = 0; action[k] = CC_ACT_WAIT;
+            if (env_ok && avalid[k]) {
+                pos[k] = pack_pos(p.x[row + aidx[k]], p.y[row + aidx[k]]);
+                fl[k] = p.flags[row + aidx[k]];
+                if (MODE == kModeStep && p.policy == CC_POLICY_EXTERNAL) action[k] = p.actions[row + aidx[k]];
+            }
+        }
+        int step = env_ok ? p.step[n] : 0;
+        float ep_ret = (env_ok && MODE == kModeStep) ? p.ep_ret[n] : 0.f;
+
+        // ---- on-device policies (baseline_policies/*.py at randomness_factor 0) ---------------
+        if ((MODE == kModeStep || MODE == kModePolicy) && p.policy != CC_POLICY_EXTERNAL) {
+            if (p.policy == CC_POLICY_RANDOM) {
+#pragma unroll
+                for (int k = 0; k < APL; ++k)
+                    if (env_ok && avalid[k]) action[k] = bounded(draw(p, genv, kStreamAction, (unsigned)aidx[k]).v0, 5);
+            } else {
+                // occupancy grid of ACTIVE agents in shared memory (collectivecrossing.py:536-541
+                // as a bit test; the asking agent's own cell is never a neighbour cell)
+                const int stride = p.W + 1;
+                for (int w = T.li; w < p.bitmap_words; w += LPE) bitmap[w] = 0u;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < APL; ++k)
+                    if (env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE)) {
+                        int x = pos_x(pos[k]), y = pos_y(pos[k]);
+                        if ((unsigned)x <= (unsigned)p.W && (unsigned)y <= (unsigned)p.H) {
+                            int b = y * stride + x;
+                            atomicOr(&bitmap[b >> 5], 1u << (b & 31));
+                        }
+                    }
+                __syncwarp();
+                // waiting_policy.py:118-131: some exiting agent that is not done has not arrived
+                bool pending = false;
+#pragma unroll
+                for (int k = 0; k < APL; ++k)
+                    pending |= env_ok && avalid[k] && aidx[k] >= p.B && !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED)) &&
+                               pos_y(pos[k]) != p.YE;
+                const bool exiting_pending = T.tballot(pending) != 0u;
+#pragma unroll
+                for (int k = 0; k < APL; ++k) {
+                    int a = CC_ACT_WAIT;
+                    const bool asks = env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE) && !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED));
+                    if (asks) {
+                        const int x = pos_x(pos[k]), y = pos_y(pos[k]);
+                        const bool boarding = aidx[k] < p.B;
+                        const bool waits = p.policy == CC_POLICY_WAITING && boarding && !in_tram_area(p, x, y) && exiting_pending;
+                        if (!waits) {
+                            // validity of the four moves (greedy_policy.py:238-264 -> _is_move_valid)
+                            unsigned vmask = 0;
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) {
+                                int nx = x + act_dx(m), ny = y + act_dy(m);
+                                bool ok = valid_position(p, nx, ny);
+                                if (ok) { int b = ny * stride + nx; ok = !((bitmap[b >> 5] >> (b & 31)) & 1u); }
+                                vmask |= ok ? (1u << m) : 0u;
+                            }
+                            // greedy_policy.py:90-161 _calculate_direction (+ :163-236)
+                            int dx = 0, dy = 0;
+                            const int D = p.D, dc = p.DC;
+                            auto sgn = [](int v) { return (v > 0) - (v < 0); };
+                            unsigned pref;  // fallback list, 4 nibbles, first choice lowest (greedy_policy.py:311-449)
+                            if (boarding) {
+                                if (y < D) {
+                                    if (y == D - 1) { if (x == dc) dy = 1; else dx = sgn(dc - x); }
+                                    else dy = 1;
+                                    pref = (x < dc) ? 0x3210u : (x > dc) ? 0x3012u : 0x3201u;  // RULD | LURD | URLD
+                                } else { dy = sgn(p.YB - y); pref = 0x3201u; }
+                            } else {
+                                if (y > D) {
+                                    if (y == D + 1) { if (x == dc) dy = -1; else dx = sgn(dc - x); }
+                                    else dy = -1;
+                                    pref = (x < dc) ? 0x1230u : (x > dc) ? 0x1032u : 0x1203u;  // RDLU | LDRU | DRLU
+                                } else { dy = sgn(p.YE - y); pref = 0x1203u; }
+                            }
+                            int want = dx == 1 ? CC_ACT_RIGHT : dx == -1 ? CC_ACT_LEFT : dy == 1 ? CC_ACT_UP : dy == -1 ? CC_ACT_DOWN : CC_ACT_WAIT;
+                            if (want == CC_ACT_WAIT || ((vmask >> want) & 1u)) a = want;
+                            else {
+                                a = CC_ACT_WAIT;
+#pragma unroll
+                                for (int c = 3; c >= 0; --c) { int cand = (pref >> (4 * c)) & 15; if ((vmask >> cand) & 1u) a = cand; }
+                            }
+                        }
+                    }
+                    action[k] = a;
+                }
+                __syncwarp();
+            }
+        }
+        if (MODE == kModePolicy) {
+#pragma unroll
+            for (int k = 0; k < APL; ++k)
+                if (env_ok && avalid[k]) p.actions_out[row + aidx[k]] = (int8_t)action[k];
+            continue;
+        }
+
+        bool need_reset = false;
+        unsigned eflags = 0;
+        if (MODE == kModeStep) {
+            if (p.actions_out) {
+#pragma unroll
+                for (int k = 0; k < APL; ++k)
+                    if (env_ok && avalid[k]) p.actions_out[row + aidx[k]] = (int8_t)action[k];
+            }
+            // ---- collectivecrossing.py:188 ---------------------------------------------------
+            step += 1;
+            bool alive_prev[APL];
+#pragma unroll
+            for (int k = 0; k < APL; ++k) alive_prev[k] = avalid[k] && !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED));
+
+            // ---- collectivecrossing.py:197-202: ordered moves -------------------------------
+            if (p.order == nullptr) {
+                // every agent has an entry: :707-711 applies to all of them
+#pragma unroll
+                for (int k = 0; k < APL; ++k)
+                    if (env_ok && avalid[k] && (unsigned)action[k] > 4u) errbits |= kErrInvalidAction;
+                unsigned req[APL];
+#pragma unroll
+                for (int k = 0; k < APL; ++k) req[k] = move_request(p, pos[k], action[k], env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE));
+#pragma unroll
+                for (int s = 0; s < APL; ++s) {
+                    const int lim = min(LPE, A - s * LPE);
+#pragma unroll 8
+                    for (int l = 0; l < lim; ++l) {
+                        const unsigned rq = T.tshfl(req[s], l);
+                        bool hit = false;  // :536-541 another ACTIVE agent on the target cell
+#pragma unroll
+                        for (int k = 0; k < APL; ++k)
+                            hit |= avalid[k] && (fl[k] & CC_F_ACTIVE) && pos[k] == (rq & 0xffffu) && !(k == s && T.li == l);
+                        const unsigned occ = T.tballot(hit);
+                        if (T.li == l && (rq >> 31) && !occ) pos[s] = rq & 0xffffu;  // :406-408
+                    }
+                }
+            } else {
+                int ord[APL];
+#pragma unroll
+                for (int k = 0; k < APL; ++k) ord[k] = (env_ok && avalid[k]) ? (int)p.order[row + aidx[k]] : -1;
+                bool stop = !env_ok;
+                for (int k = 0; k < A; ++k) {
+                    const int oi = (int)T.tshfl((unsigned)picki<APL>(ord, k >> TL_::LOG), k & (LPE - 1));
+                    stop = stop || oi < 0;
+                    bool live = !stop;
+                    if (live && oi >= A) { errbits |= kErrInvalidAction; live = false; }  // :701-705
+                    const int ol = oi & (LPE - 1), os = oi >> TL_::LOG;
+                    const int my_act = picki<APL>(action, os);
+                    const unsigned my_pos = pick<APL>(pos, os);
+                    const unsigned my_fl = pick<APL>(fl, os);
+                    const bool owner = live && T.li == ol;
+                    if (owner && (unsigned)my_act > 4u) errbits |= kErrInvalidAction;   // :707-711
+                    unsigned rq = T.tshfl(move_request(p, my_pos, my_act, (my_fl & CC_F_ACTIVE) != 0), ol);
+                    if (!live) rq = 0;
+                    bool hit = false;
+#pragma unroll
+                    for (int s = 0; s < APL; ++s)
+                        hit |= avalid[s] && (fl[s] & CC_F_ACTIVE) && pos[s] == (rq & 0xffffu) && !(s == os && T.li == ol);
+                    const unsigned occ = T.tballot(hit);
+                    if (owner && (rq >> 31) && !occ) {
+#pragma unroll
+                        for (int s = 0; s < APL; ++s) if (s == os) pos[s] = rq & 0xffffu;
+                    }
+                }
+            }
+
+            // ---- :210-212 deactivate arrivals; rewards; terminated; truncated --------------
+            bool arr[APL];
+            int n_arrived_now = 0;
+            bool lane_all_arr = true;
+#pragma unroll
+            for (int k = 0; k < APL; ++k) {
+                const int dest = aidx[k] < p.B ? p.YB : p.YE;          // :663-683 (y only)
+                arr[k] = avalid[k] && pos_y(pos[k]) == dest;
+                const bool newly = arr[k] && (fl[k] & CC_F_ACTIVE);
+                if (newly) fl[k] &= ~(unsigned)CC_F_ACTIVE;            // types.py:46-51
+                n_arrived_now += __popc(T.tballot(env_ok && newly));
+                lane_all_arr = lane_all_arr && (arr[k] || !avalid[k]);
+            }
+            const bool all_arrived = T.tballot(!lane_all_arr) == 0u;
+            const bool over_limit = step >= p.max_steps;                // truncateds.py:61
+            bool lane_alive = false;
+            float rsum_lane = 0.f;
+            double rew[APL];
+            unsigned oflag[APL];
+#pragma unroll
+            for (int k = 0; k < APL; ++k) {
+                const int x = pos_x(pos[k]), y = pos_y(pos[k]);
+                const bool boarding = aidx[k] < p.B;
+                double r = 0.0;
+                if (alive_prev[k]) {                                    // rewards.py:65-66 etc.
+                    switch (p.reward_kind) {
+                    case CC_REWARD_DEFAULT:                             // rewards.py:68-99
+                        if (boarding) {
+                            if (arr[k]) r = p.rp[0];
+                            else if (at_tram_door(p, x, y)) r = p.rp[1];
+                            else if (in_tram_area(p, x, y)) r = p.rp[2];
+                            else r = (double)(-(abs(x - p.DC) + (p.D - y))) * p.rp[3];
+                        } else {
+                            if (arr[k]) r = p.rp[0];
+                            else if (!in_tram_area(p, x, y)) r = p.rp[2];
+                            else r = (double)(abs(x - p.DC) + (y - p.D)) * p.rp[3];
+                        }
+                        break;
+                    case CC_REWARD_SIMPLE_DISTANCE:                     // rewards.py:120-129
+                        r = (double)(-abs(y - (boarding ? p.YB : p.YE))) * p.rp[0];
+                        break;
+                    case CC_REWARD_BINARY: r = p.rp[1]; break;          // rewards.py:152-159 (never goal_reward)
+                    default: r = p.rp[0]; break;                        // rewards.py:179-182
+                    }
+                }
+                rew[k] = r;
+                rsum_lane += (float)r;
+                lane_alive |= alive_prev[k];
+                const bool tval = (p.terminated_kind == CC_TERM_ALL_AT_DESTINATION) ? all_arrived : arr[k];  // terminateds.py:56-60,82
+                const bool cval = alive_prev[k] && over_limit;          // truncateds.py:57-61
+                bool newly_done = false;                                // collectivecrossing.py:229-241
+                if (tval && !(fl[k] & CC_F_TERMINATED)) { fl[k] |= CC_F_TERMINATED; newly_done = true; }
+                if (cval && !(fl[k] & CC_F_TRUNCATED)) { fl[k] |= CC_F_TRUNCATED; newly_done = true; }
+                const bool present = !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED)) || newly_done;  // :243
+                oflag[k] = (fl[k] & 7u) | (alive_prev[k] ? CC_O_ALIVE_PREV : 0u) | (tval ? CC_O_TERM_VALUE : 0u) |
+                           (cval ? CC_O_TRUNC_VALUE : 0u) | (present ? CC_O_OBS_PRESENT : 0u);
+            }
+            const bool any_alive = T.tballot(lane_alive) != 0u;
+            const bool term_all = all_arrived;                          // :256 (terminateds holds every agent)
+            const bool trunc_all = any_alive && over_limit;             // :257
+            // reward sum: balanced tree over the tile's lanes (fixed association order; the oracle
+            // reproduces it), accumulated into the env's float32 episode return
+            float rsum = rsum_lane;
+#pragma unroll
+            for (int w = LPE / 2; w >= 1; w >>= 1) rsum += __shfl_xor_sync(kFull, rsum, w, LPE);
+            ep_ret += rsum;
+            const bool done = term_all || trunc_all;
+            eflags = (term_all ? CC_E_TERMINATED_ALL : 0u) | (trunc_all ? CC_E_TRUNCATED_ALL : 0u);
+
+            // ---- outputs of the finished step ----------------------------------------------
+#pragma unroll
+            for (int k = 0; k < APL; ++k)
+                if (env_ok && avalid[k]) {
+                    const long long o = row + aidx[k];
+                    if (p.reward_f64) reinterpret_cast<double *>(p.reward)[o] = rew[k];
+                    else reinterpret_cast<float *>(p.reward)[o] = (float)rew[k];
+                    p.agent_flags[o] = (uint8_t)oflag[k];
+                    if (p.agent_info) {                                 // :248-254
+                        const int x = pos_x(pos[k]), y = pos_y(pos[k]);
+                        p.agent_info[o] = (uint8_t)((in_tram_area(p, x, y) ? CC_I_IN_TRAM_AREA : 0) | (at_tram_door(p, x, y) ? CC_I_AT_DOOR : 0) |
+                                                    ((fl[k] & CC_F_ACTIVE) ? CC_I_ACTIVE : 0) | (arr[k] ? CC_I_AT_DESTINATION : 0));
+                    }
+                }
+            if (env_ok && T.li == 0) {
+                st_steps += 1;
+                st_arrivals += n_arrived_now;
+                st_rsum += (double)rsum;
+                if (done && any_alive) {
+                    st_episodes += 1; st_term += term_all; st_trunc += trunc_all;
+                    st_eplen += step; st_epret += (double)ep_ret;
+                }
+            }
+            need_reset = env_ok && done && p.auto_reset;
+            if (need_reset) { eflags |= CC_E_WAS_RESET; ep_ret = 0.f; }
+        }
+        if (MODE == kModeReset) need_reset = env_ok && (p.mask == nullptr || p.mask[n] != 0);
+
+        // ---- collectivecrossing.py:91-150 reset(): rejection-sampled placement ---------------
+        // Agent i's k-th candidate is Philox(seed; genv, t, RESET, i<<16|k); it takes the first
+        // candidate that passes the geometric test and is not occupied by an agent j < i.  The
+        // candidates are drawn by all lanes at once, the acceptance sweep is sequential.
+        if ((MODE == kModeStep || MODE == kModeReset) && __any_sync(kFull, need_reset)) {
+            bool placed[APL], has_cand[APL];
+            unsigned cand[APL];
+            int attempt[APL];
+#pragma unroll
+            for (int k = 0; k < APL; ++k) { placed[k] = false; has_cand[k] = false; cand[k] = 0; attempt[k] = 0; }
+            int fin = need_reset ? 0 : A;  // agents finalised so far (tile-uniform)
+            while (__any_sync(kFull, fin < A)) {
+#pragma unroll
+                for (int k = 0; k < APL; ++k) {
+                    if (fin < A && avalid[k] && !placed[k] && !has_cand[k]) {
+                        const U4 r = draw(p, genv, kStreamReset, ((unsigned)aidx[k] << 16) | (unsigned)attempt[k]);
+                        int cx, cy;
+                        bool ok;
+                        if (aidx[k] < p.B) {                            // :103-117
+                            cx = bounded(r.v0, p.W); cy = bounded(r.v1, p.D);
+                            ok = valid_position(p, cx, cy) && !(p.DL <= cx && cx <= p.DR && cy == p.D - 1);
+                        } else {                                        // :132-140
+                            cx = p.TL + bounded(r.v0, p.TR + 1 - p.TL); cy = p.D + bounded(r.v1, p.H - p.D);
+                            ok = valid_position(p, cx, cy);
+                        }
+                        attempt[k] += 1;
+                        cand[k] = pack_pos(cx, cy);
+                        has_cand[k] = ok;
+                        if (!ok && attempt[k] >= kResetAttemptCap) { has_cand[k] = true; cand[k] |= 0x10000u; errbits |= kErrResetStuck; }
+                    }
+                }
+                bool progress = true;
+                while (__any_sync(kFull, progress && fin < A)) {
+                    const bool act_tile = progress && fin < A;
+                    const int fi = act_tile ? fin : 0;
+                    const int ol = fi & (LPE - 1), os = fi >> TL_::LOG;
+                    unsigned mine = pick<APL>(cand, os);
+                    bool mine_has = false;
+#pragma unroll
+                    for (int s = 0; s < APL; ++s) mine_has = (s == os) ? has_cand[s] : mine_has;
+                    const unsigned rq = T.tshfl(mine | (mine_has ? 0x80000000u : 0u), ol);
+                    const bool forced = (rq & 0x10000u) != 0;  // attempt cap hit: place regardless
+                    bool hit = false;
+#pragma unroll
+                    for (int s = 0; s < APL; ++s) hit |= placed[s] && pos[s] == (rq & 0xffffu);
+                    const unsigned occ = T.tballot(hit);
+                    if (act_tile && (rq >> 31)) {
+                        if (!occ || forced) {
+                            if (T.li == ol) {
+#pragma unroll
+                                for (int s = 0; s < APL; ++s) if (s == os) { placed[s] = true; pos[s] = rq & 0xffffu; }
+                            }
+                            fin += 1;
+                        } else {
+                            if (T.li == ol) {
+#pragma unroll
+                                for (int s = 0; s < APL; ++s)
+                                    if (s == os) {
+                                        has_cand[s] = false;
+                                        if (attempt[s] >= kResetAttemptCap) { has_cand[s] = true; cand[s] |= 0x10000u; errbits |= kErrResetStuck; }
+                                    }
+                            }
+                            progress = false;
+                        }
+                    } else progress = false;
+                }
+            }
+            if (need_reset) {
+                step = 0;                                               // :97
+#pragma unroll
+                for (int k = 0; k < APL; ++k) fl[k] = avalid[k] ? (unsigned)CC_F_ACTIVE : 0u;
+                if (MODE == kModeReset) ep_ret = 0.f;
+            }
+        }
+
+        // ---- write back the persistent state ----------------------------------------------------
+        if (MODE == kModeStep || MODE == kModeReset) {
+            const bool wr = env_ok && (MODE == kModeStep || need_reset);
+#pragma unroll
+            for (int k = 0; k < APL; ++k)
+                if (wr && avalid[k]) {
+                    p.x[row + aidx[k]] = (int8_t)pos_x(pos[k]);
+                    p.y[row + aidx[k]] = (int8_t)pos_y(pos[k]);
+                    p.flags[row + aidx[k]] = (uint8_t)(fl[k] & 7u);
+                }
+            if (wr && T.li == 0) {
+                p.step[n] = step;
+                p.ep_ret[n] = ep_ret;
+                if (MODE == kModeStep) p.env_flags[n] = (uint8_t)eflags;
+            }
+        }
+
+        // ---- observations.py:43-94 from the post-step (post-reset) state ------------------------
+        if (OBS != CC_OBS_NONE && p.obs != nullptr) {
+            P2 *tstage = stage + 3 + T.tile * 2 * A;
+#pragma unroll
+            for (int k = 0; k < APL; ++k)
+                if (avalid[k]) {
+                    tstage[2 * aidx[k]] = mk_pair<OT>(pos_x(pos[k]), pos_y(pos[k]));
+                    tstage[2 * aidx[k] + 1] = mk_pair<OT>(aidx[k] < p.B ? 0 : 1, (fl[k] & CC_F_ACTIVE) ? 1 : 0);
+                }
+            __syncwarp();
+            const long long n0 = g * EPW;
+            if (MODE == kModeReset) {
+                // only the envs that were reset get their rows rewritten
+                const unsigned tiles = __ballot_sync(kFull, need_reset);
+#pragma unroll
+                for (int e = 0; e < EPW; ++e)
+                    if ((tiles >> (e * LPE)) & 1u)
+                        emit_obs<OT>(reinterpret_cast<OT *>(p.obs), (n0 + e) * (long long)p.pairs_per_env, p.pairs_per_env,
+                                     lut + e * p.pairs_per_env, stage, T.lane);
+            } else {
+                const long long rem = p.n_envs - n0;
+                const int envs_here = rem < EPW ? (int)rem : EPW;
+                emit_obs<OT>(reinterpret_cast<OT *>(p.obs), n0 * (long long)p.pairs_per_env, envs_here * p.pairs_per_env, lut, stage, T.lane);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- statistics: warp shuffle -> shared memory -> one atomic per slot per CTA -----------------
+    if (MODE == kModeStep) {
+        unsigned long long *red = reinterpret_cast<unsigned long long *>(smem + p.off_red);
+        long long iv[6] = {st_steps, st_episodes, st_term, st_trunc, st_arrivals, st_eplen};
+        double dv[2] = {st_epret, st_rsum};
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) iv[i] += __shfl_xor_sync(kFull, iv[i], w);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) dv[i] += __shfl_xor_sync(kFull, dv[i], w);
+        }
+        __syncthreads();  // smem may still be read as LUT / stage by slower warps
+        if (T.lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) red[warp * kStCount + i] = (unsigned long long)iv[i];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) red[warp * kStCount + 6 + i] = (unsigned long long)__double_as_longlong(dv[i]);
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            long long s = 0;
+            for (int w = 0; w < kWarpsPerCta; ++w) s += (long long)red[w * kStCount + threadIdx.x];
+            if (s) atomicAdd(&p.stats[threadIdx.x], (unsigned long long)s);
+        } else if (threadIdx.x < 8) {
+            double s = 0.0;
+            for (int w = 0; w < kWarpsPerCta; ++w) s += __longlong_as_double((long long)red[w * kStCount + threadIdx.x]);
+            if (s != 0.0) atomicAdd(reinterpret_cast<double *>(&p.stats[threadIdx.x]), s);
+        }
+    }
+    if (errbits) atomicOr(p.err, errbits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset(seed=s), bit-exact with the reference's generator: numpy Generator(PCG64(SeedSequence(s)))
+// (gymnasium seeding; collectivecrossing.py:95,105-106,134-137).  One thread per env — the draw
+// stream is inherently sequential.  Restated from numpy's bit_generator.pyx (SeedSequence),
+// _pcg64 / pcg64.h (seeding, XSL-RR 128/64 output, 32-bit buffering) and distributions.c
+// (Lemire bounded uint32), see oracle/cc_oracle.c for the CPU twin.
+// ---------------------------------------------------------------------------------------------
+struct Pcg64 {
+    unsigned long long hi, lo, inc_hi, inc_lo;
+    unsigned buffered;
+    bool has_buffered;
+    __device__ __forceinline__ void advance() {
+        const unsigned long long MH = 2549297995355413924ULL, ML = 4865540595714422341ULL;
+        unsigned long long nlo = lo * ML;
+        unsigned long long nhi = __umul64hi(lo, ML) + hi * ML + lo * MH;
+        unsigned long long slo = nlo + inc_lo;
+        nhi += inc_hi + (slo < nlo ? 1ULL : 0ULL);
+        hi = nhi; lo = slo;
+    }
+    __device__ __forceinline__ unsigned long long next64() {
+        advance();
+        unsigned long long v = hi ^ lo;
+        unsigned rot = (unsigned)(hi >> 58);
+        return (v >> rot) | (v << ((64u - rot) & 63u));
+    }
+    __device__ __forceinline__ unsigned next32() {
+        if (has_buffered) { has_buffered = false; return buffered; }
+        unsigned long long n = next64();
+        has_buffered = true; buffered = (unsigned)(n >> 32);
+        return (unsigned)n;
+    }
+    __device__ __forceinline__ long long integers(long long low, long long high) {  // [low, high)
+        unsigned rng = (unsigned)(high - low) - 1u;
+        if (rng == 0u) return low;
+        unsigned excl = rng + 1u;
+        unsigned long long m = (unsigned long long)next32() * excl;
+        unsigned left = (unsigned)m;
+        if (left < excl) {
+            unsigned thr = (0xFFFFFFFFu - rng) % excl;
+            while (left < thr) { m = (unsigned long long)next32() * excl; left = (unsigned)m; }
+        }
+        return low + (long long)(m >> 32);
+    }
+    __device__ void seed(unsigned long long s) {
+        unsigned ent[2] = {(unsigned)s, (unsigned)(s >> 32)};
+        int n_ent = (s >> 32) ? 2 : 1;
+        unsigned pool[4], hc = 0x43b0d7e5u;
+        auto hashmix = [&](unsigned v) { v ^= hc; hc *= 0x931e8875u; v *= hc; v ^= v >> 16; return v; };
+        auto mix = [](unsigned a, unsigned b) { unsigned r = 0xca01f9ddu * a - 0x4973f715u * b; r ^= r >> 16; return r; };
+        for (int i = 0; i < 4; ++i) pool[i] = hashmix(i < n_ent ? ent[i] : 0u);
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b)
+                if (a != b) pool[b] = mix(pool[b], hashmix(pool[a]));
+        unsigned st[8], hb = 0x8b51f9ddu;
+        for (int i = 0; i < 8; ++i) { unsigned v = pool[i & 3]; v ^= hb; hb *= 0x58f38dedu; v *= hb; v ^= v >> 16; st[i] = v; }
+        unsigned long long w0 = st[0] | ((unsigned long long)st[1] << 32), w1 = st[2] | ((unsigned long long)st[3] << 32);
+        unsigned long long w2 = st[4] | ((unsigned long long)st[5] << 32), w3 = st[6] | ((unsigned long long)st[7] << 32);
+        // pcg_setseq_128_srandom_r(initstate = w0:w1, initseq = w2:w3)
+        inc_hi = (w2 << 1) | (w3 >> 63); inc_lo = (w3 << 1) | 1ULL;
+        hi = 0; lo = 0;
+        advance();
+        unsigned long long slo = lo + w1;
+        hi += w0 + (slo < lo ? 1ULL : 0ULL); lo = slo;
+        advance();
+        has_buffered = false; buffered = 0;
+    }
+};
+
+__global__ void __launch_bounds__(128) cc_reset_seeded_kernel(const __grid_constant__ KParams p, const long long *seeds) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.n_envs) return;
+    Pcg64 g;
+    g.seed((unsigned long long)seeds[n]);
+    int8_t *x = p.x + n * p.A, *y = p.y + n * p.A;
+    int stuck = 0;
+    for (int i = 0; i < p.A; ++i) {
+        int px = 0, py = 0;
+        bool ok = false;
+        for (int attempt = 0; attempt < kResetAttemptCap && !ok; ++attempt) {
+            if (i < p.B) {
+                px = (int)g.integers(0, p.W); py = (int)g.integers(0, p.D);
+                ok = valid_position(p, px, py) && !(p.DL <= px && px <= p.DR && py == p.D - 1);
+            } else {
+                px = (int)g.integers(p.TL, p.TR + 1); py = (int)g.integers(p.D, p.H);
+                ok = valid_position(p, px, py);
+            }
+            for (int j = 0; ok && j < i; ++j) ok = !(x[j] == px && y[j] == py);
+        }
+        if (!ok) stuck = 1;
+        x[i] = (int8_t)px; y[i] = (int8_t)py;
+        p.flags[n * p.A + i] = CC_F_ACTIVE;
+    }
+    p.step[n] = 0;
+    p.ep_ret[n] = 0.f;
+    if (stuck) atomicOr(p.err, kErrResetStuck);
+}
+
+}  // namespace ccb

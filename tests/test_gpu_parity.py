@@ -1,0 +1,334 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the golden vectors.
+Bit-exact for positions, flags, integer observations, infos and — because the kernel computes
+rewards in float64 and rounds once — also for float32/float64 rewards."""
+
+import numpy as np
+import pytest
+from cases import GOLDEN_CASES, cassette_config, crew_config, large_config, readme_config
+from helpers import CASSETTE_BITS, assert_same, load_golden, random_states, replay_device
+
+from collectivecrossing_b200 import _abi
+from collectivecrossing_b200.lowering import lower_config
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+POLICY_CASES = [n for n, (_, kw) in GOLDEN_CASES.items() if kw["source"] in ("greedy", "waiting")]
+
+
+def make_env(cfg, n, **kw):
+    from collectivecrossing_b200 import BatchedCollectiveCrossing
+
+    return BatchedCollectiveCrossing(cfg, n, "cuda:0", **kw)
+
+
+# ---- golden vectors (reference outputs) ----------------------------------------------------------
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_device_replays_golden(name):
+    cfg = GOLDEN_CASES[name][0]()
+    rec = load_golden(name)
+    assert_same(rec, replay_device(cfg, rec), f"device/{name}")
+
+
+@pytest.mark.parametrize("name", POLICY_CASES)
+def test_device_policies_match_reference_policies(name):
+    cfg, kw = GOLDEN_CASES[name][0](), GOLDEN_CASES[name][1]
+    rec = load_golden(name)
+    assert_same(rec, replay_device(cfg, rec, policy=kw["source"]), f"device-policy/{name}", policy_actions=True)
+
+
+@pytest.mark.parametrize("name", ["cassette_basic", "cassette_regression"])
+def test_device_replays_reference_cassettes(name):
+    rec = load_golden(name)
+    assert_same(rec, replay_device(cassette_config(), rec), f"device/{name}", flag_mask=CASSETTE_BITS)
+
+
+def test_device_fp32_outputs_match_golden_within_tolerance():
+    """float32 observations are the same integers; float32 rewards within 1e-6 relative of the
+    reference's float64 (north_star tolerance)."""
+    name = "readme_random"
+    cfg, rec = GOLDEN_CASES[name][0](), load_golden(name)
+    got = replay_device(cfg, rec, obs_dtype="float32", reward_dtype="float32")
+    assert_same(rec, got, "device-fp32", reward_rtol=1e-6)
+
+
+# ---- seeded comparison against the oracle, every kernel instantiation ----------------------------
+ORACLE_CASES = {
+    "A1": (lambda: crew_config(1, 0, max_steps=25), 37),
+    "A3_cassette": (cassette_config, 101),
+    "A5": (lambda: crew_config(3, 2, max_steps=40, term="all"), 258),
+    "A8_readme": (lambda: readme_config(max_steps=60), 1031),
+    "A12": (lambda: crew_config(7, 5, max_steps=40, reward="simple_distance"), 130),
+    "A21_odd": (lambda: crew_config(13, 8, max_steps=40), 67),
+    "A40": (lambda: crew_config(25, 15, max_steps=40, reward="binary"), 33),
+    "A64_large": (lambda: large_config(40), 19),
+    "A100": (lambda: crew_config(60, 40, max_steps=30, reward="constant_negative", term="all"), 9),
+}
+
+
+def _compare_step(env, orc, res, out, tag, obs_np):
+    for k, a, b in (("x", env.x, orc.x), ("y", env.y, orc.y), ("flags", env.flags, orc.flags),
+                    ("step", env.step_count, orc.step_count), ("episode_return", env.episode_return, orc.episode_return)):
+        assert np.array_equal(a.cpu().numpy(), b), f"{tag}: state {k} differs"
+    assert np.array_equal(out.reward.cpu().numpy(), res["reward"]), f"{tag}: reward"
+    assert np.array_equal(out.agent_flags.cpu().numpy(), res["agent_flags"]), f"{tag}: agent_flags"
+    assert np.array_equal(out.agent_info.cpu().numpy(), res["agent_info"]), f"{tag}: agent_info"
+    assert np.array_equal(out.env_flags.cpu().numpy(), res["env_flags"]), f"{tag}: env_flags"
+    assert np.array_equal(out.actions.cpu().numpy(), res["actions_out"]), f"{tag}: actions"
+    assert np.array_equal(out.obs.cpu().numpy().astype(obs_np), res["obs"]), f"{tag}: obs"
+
+
+@pytest.mark.parametrize("policy", ["random", "greedy", "waiting"])
+@pytest.mark.parametrize("case", list(ORACLE_CASES))
+def test_device_matches_oracle_with_auto_reset(case, policy):
+    """Same seeded start states, on-device policy, auto-reset on: every step, every field."""
+    import oracle
+
+    make_cfg, n = ORACLE_CASES[case]
+    cfg = make_cfg()
+    low = lower_config(cfg)
+    rng = np.random.default_rng(hash((case, policy)) % 2**32)
+    x, y, f, s = random_states(cfg, n, rng)
+    seed, offset = 1234567 + n, 10_000_000_000 + n  # offset > 2**32: both counter words matter
+    obs_dtype = "float32" if policy == "greedy" else "int8"
+    env = make_env(cfg, n, seed=seed, global_env_offset=offset, obs_dtype=obs_dtype, auto_reset=True, with_info=True)
+    orc = oracle.OracleEnvs(low, n, seed=seed, global_env_offset=offset)
+    env.set_state(*(torch.from_numpy(v).cuda() for v in (x, y, f, s)))
+    orc.set_state(x, y, f, s)
+    steps = 70 if low.num_agents <= 21 else 45
+    for t in range(steps):
+        out = env.step(policy=policy)
+        res = orc.step(policy=policy, auto_reset=True, obs_dtype=_abi.OBS_FP32 if obs_dtype == "float32" else _abi.OBS_INT8)
+        _compare_step(env, orc, res, out, f"{case}/{policy}/t={t}", np.float32 if obs_dtype == "float32" else np.int8)
+    env.check_error()
+    st, want = env.stats(), orc.stats.as_dict()
+    for k in ("env_steps", "episodes", "terminated_all", "truncated_all", "arrivals", "episode_length_sum"):
+        assert st[k] == want[k], (k, st[k], want[k])
+    for k in ("episode_return_sum", "reward_sum"):
+        assert st[k] == pytest.approx(want[k], rel=1e-9, abs=1e-9), k
+    assert st["episodes"] > 0 or low.max_steps > steps
+
+
+@pytest.mark.parametrize("case", ["A5", "A8_readme", "A21_odd", "A64_large"])
+def test_device_external_actions_and_custom_order_match_oracle(case):
+    """Random action tensors incl. partial lists in shuffled dict order, no auto-reset."""
+    import oracle
+
+    make_cfg, n = ORACLE_CASES[case]
+    cfg = make_cfg()
+    low = lower_config(cfg)
+    A = low.num_agents
+    rng = np.random.default_rng(99)
+    x, y, f, s = random_states(cfg, n, rng)
+    env = make_env(cfg, n, obs_dtype="int8", reward_dtype="float64", auto_reset=False, with_info=True)
+    orc = oracle.OracleEnvs(low, n)
+    env.set_state(*(torch.from_numpy(v).cuda() for v in (x, y, f, s)))
+    orc.set_state(x, y, f, s)
+    for t in range(50):
+        acts = rng.integers(0, 5, size=(n, A)).astype(np.int8)
+        order = np.full((n, A), -1, np.int8)
+        for e in range(n):
+            k = int(rng.integers(0, A + 1))
+            order[e, :k] = rng.permutation(A)[:k]
+        use_order = t % 3 != 0
+        out = env.step(torch.from_numpy(acts).cuda(), order=torch.from_numpy(order).cuda() if use_order else None)
+        res = orc.step(acts, order=order if use_order else None, obs_dtype=_abi.OBS_INT8, reward_dtype=_abi.REWARD_F64)
+        _compare_step(env, orc, res, out, f"{case}/t={t}", np.int8)
+    env.check_error()
+
+
+# ---- BASELINE config 2 at full size: 65,536 envs, greedy policy, bit-exact replay ----------------
+def test_config2_65536_envs_greedy_bit_exact_vs_oracle():
+    import oracle
+
+    cfg = readme_config()
+    low = lower_config(cfg)
+    n = 65536
+    rng = np.random.default_rng(2)
+    x, y, f, s = random_states(cfg, n, rng)
+    env = make_env(cfg, n, seed=7, obs_dtype="float32", auto_reset=True, with_info=True)
+    orc = oracle.OracleEnvs(low, n, seed=7)
+    env.set_state(*(torch.from_numpy(v).cuda() for v in (x, y, f, s)))
+    orc.set_state(x, y, f, s)
+    for t in range(120):  # beyond max_steps = 100: truncation-driven auto-reset is exercised
+        out = env.step(policy="greedy")
+        res = orc.step(policy="greedy", auto_reset=True, obs_dtype=_abi.OBS_FP32)
+        if t % 10 == 9 or t >= 98:
+            _compare_step(env, orc, res, out, f"cfg2/t={t}", np.float32)
+    _compare_step(env, orc, res, out, "cfg2/final", np.float32)
+    st = env.stats()
+    assert st["episodes"] == orc.stats.episodes > 0 and st["truncated_all"] == orc.stats.truncated_all
+
+
+# ---- size-independent properties at BASELINE's large sizes ----------------------------------------
+def _check_invariants(env, cfg, out):
+    """Properties every reachable state has, evaluated with torch ops on the device."""
+    low = lower_config(cfg)
+    A, B = low.num_agents, low.num_boarding
+    x, y, fl = env.x.int(), env.y.int(), env.flags
+    active = (fl & _abi.F_ACTIVE) != 0
+    # inside the lattice, never on a wall (collectivecrossing.py:509-534)
+    assert bool(((x >= 0) & (x <= low.width) & (y >= 0) & (y <= low.height)).all())
+    on_div = y == low.division_y
+    assert bool((~on_div | ((x > low.door_left) & (x < low.door_right))).all())
+    assert bool(((y < low.division_y) | ((x > low.tram_left) & (x < low.tram_right))).all())
+    # no two ACTIVE agents share a cell
+    cell = torch.where(active, y * 128 + x, -1 - torch.arange(A, device=x.device).expand_as(x))
+    srt = cell.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    # arrived <=> inactive; step counter within bounds
+    dest = torch.where(torch.arange(A, device=x.device) < B, low.boarding_dest_y, low.exiting_dest_y)
+    assert bool(((y == dest) == ~active).all())
+    assert bool(((env.step_count >= 0) & (env.step_count <= low.max_steps)).all())
+    # observation rows are the state table with the own block masked (observations.py:62-94)
+    obs = out.obs
+    if obs is not None:
+        o = obs.float()
+        assert bool((o[:, :, 0] == x.float()).all() and (o[:, :, 1] == y.float()).all())
+        door = torch.tensor([(low.door_left + low.door_right) // 2, low.division_y, low.door_left, low.door_right], device=o.device).float()
+        assert bool((o[:, :, 2:6] == door).all())
+        tab = torch.stack([x.float(), y.float(), (torch.arange(A, device=o.device) >= B).float().expand_as(x), active.float()], dim=2)
+        want = tab[:, None, :, :].expand(-1, A, -1, -1).clone()
+        idx = torch.arange(A, device=o.device)
+        want[:, idx, idx, :] = -1.0
+        assert bool((o[:, :, 6:].reshape(want.shape) == want).all())
+
+
+def test_one_million_envs_invariants_and_shard_invariance():
+    """BASELINE config 5 shape (12x8, waiting policy, auto-reset) at 1M envs: invariants hold, the
+    episode statistics add up, and splitting the envs over two handles with global offsets gives
+    the same trajectories (the counter RNG is keyed on the global env index)."""
+    cfg = readme_config()
+    n = 1 << 20
+    whole = make_env(cfg, n, seed=5, obs_dtype="int8", auto_reset=True)
+    whole.reset()
+    halves = [make_env(cfg, n // 2, seed=5, global_env_offset=k * (n // 2), obs_dtype="int8", auto_reset=True) for k in range(2)]
+    for h in halves:
+        h.reset()
+    assert torch.equal(whole.x, torch.cat([h.x for h in halves])) and torch.equal(whole.y, torch.cat([h.y for h in halves]))
+    resets = 0
+    for t in range(64):
+        out = whole.step(policy="waiting")
+        resets += int(out.was_reset.sum())
+        for h in halves:
+            h.step(policy="waiting")
+        if t % 16 == 15:
+            _check_invariants(whole, cfg, out)
+            assert torch.equal(whole.x, torch.cat([h.x for h in halves]))
+            assert torch.equal(whole.flags, torch.cat([h.flags for h in halves]))
+            assert torch.equal(whole.obs, torch.cat([h.obs for h in halves]))
+    st = whole.stats()
+    assert st["env_steps"] == 64 * n and st["episodes"] == resets > 0
+    assert st["terminated_all"] + st["truncated_all"] >= st["episodes"]
+    parts = [h.stats() for h in halves]
+    for k in ("episodes", "arrivals", "episode_length_sum", "terminated_all", "truncated_all"):
+        assert st[k] == parts[0][k] + parts[1][k]
+    whole.check_error()
+
+
+def test_large_geometry_invariants_fp32():
+    """BASELINE config 3 shape (64x32, 64 agents, SimpleDistance, AllAtDestination), random actions."""
+    cfg = large_config(48)
+    env = make_env(cfg, 4099, seed=3, obs_dtype="float32", auto_reset=True)
+    env.reset()
+    for t in range(60):
+        out = env.step(policy="random")
+    _check_invariants(env, cfg, out)
+    st = env.stats()
+    assert st["episodes"] == st["truncated_all"] > 0  # nobody gets 64 agents home in 48 random steps
+    env.check_error()
+
+
+# ---- API behaviour -------------------------------------------------------------------------------
+def test_reset_kernel_matches_oracle_and_mask():
+    import oracle
+
+    cfg = readme_config()
+    low = lower_config(cfg)
+    n = 777
+    env = make_env(cfg, n, seed=11, global_env_offset=5, obs_dtype="int8")
+    orc = oracle.OracleEnvs(low, n, seed=11, global_env_offset=5)
+    obs = env.reset()
+    want = orc.reset()
+    assert np.array_equal(env.x.cpu().numpy(), orc.x) and np.array_equal(env.y.cpu().numpy(), orc.y)
+    assert np.array_equal(obs.cpu().numpy(), want)
+    mask = (np.arange(n) % 3 == 0).astype(np.uint8)
+    before = env.x.clone()
+    env.reset(torch.from_numpy(mask).cuda())
+    orc.reset(mask)
+    assert np.array_equal(env.x.cpu().numpy(), orc.x) and np.array_equal(env.flags.cpu().numpy(), orc.flags)
+    assert torch.equal(env.x[1::3], before[1::3])
+
+
+@pytest.mark.parametrize("name", ["readme_random", "large_random", "crew_60_40"])
+def test_reset_seeded_is_bit_exact_with_reference_reset(name):
+    """reset(seed) on the device == the reference's reset(seed) (golden initial states)."""
+    cfg, rec = GOLDEN_CASES[name][0](), load_golden(name)
+    env = make_env(cfg, len(rec["seeds"]), obs_dtype="int8")
+    obs = env.reset_seeded(torch.from_numpy(rec["seeds"]).cuda())
+    assert np.array_equal(env.x.cpu().numpy(), rec["init_x"]) and np.array_equal(env.y.cpu().numpy(), rec["init_y"])
+    assert np.array_equal(obs.cpu().numpy(), rec["init_obs"])
+
+
+def test_invalid_action_raises_value_error():
+    cfg = readme_config()
+    env = make_env(cfg, 16, auto_reset=False)
+    env.reset()
+    acts = torch.full((16, 8), 4, dtype=torch.int8, device="cuda")
+    env.step(acts)
+    env.check_error()
+    acts[3, 2] = 7
+    env.step(acts)
+    with pytest.raises(ValueError, match="Invalid action"):
+        env.check_error()
+    env.check_error()  # cleared
+
+
+def test_step_host_equals_device_path():
+    cfg = readme_config()
+    n = 513
+    a = make_env(cfg, n, seed=1, obs_dtype="float32", with_info=True)
+    b = make_env(cfg, n, seed=1, obs_dtype="float32", with_info=True)
+    a.reset(); b.reset()
+    host = b.make_host_buffers()
+    rng = np.random.default_rng(0)
+    for t in range(30):
+        acts = torch.from_numpy(rng.integers(0, 5, size=(n, 8)).astype(np.int8))
+        out = a.step(acts.cuda())
+        host["actions"].copy_(acts)
+        b.step_host(host)
+        assert torch.equal(out.obs.cpu(), host["obs"]) and torch.equal(out.reward.cpu(), host["reward"])
+        assert torch.equal(out.agent_flags.cpu(), host["agent_flags"]) and torch.equal(out.env_flags.cpu(), host["env_flags"])
+        assert torch.equal(out.agent_info.cpu(), host["agent_info"])
+    assert torch.equal(a.x, b.x)
+
+
+def test_checkpoint_resume_reproduces_trajectory():
+    cfg = readme_config(max_steps=30)
+    env = make_env(cfg, 300, seed=9, obs_dtype="int8")
+    env.reset()
+    env.rollout(17, policy="waiting")
+    snap = env.get_state()
+    env.rollout(25, policy="waiting")
+    want = (env.x.clone(), env.flags.clone(), env.step_count.clone(), env.episode_return.clone())
+    other = make_env(cfg, 300, seed=9, obs_dtype="int8")
+    other.load_state(snap)
+    other.rollout(25, policy="waiting")
+    for u, v in zip(want, (other.x, other.flags, other.step_count, other.episode_return)):
+        assert torch.equal(u, v)
+
+
+def test_policy_actions_kernel_matches_step_policy():
+    cfg = readme_config()
+    env = make_env(cfg, 1000, seed=2, obs_dtype="none")
+    env.reset()
+    env.rollout(9, policy="greedy")
+    for pol in ("greedy", "waiting", "random"):
+        standalone = env.policy_actions(pol, out=torch.zeros((1000, 8), dtype=torch.int8, device="cuda")).clone()
+        snap = env.get_state()
+        applied = env.step(policy=pol).actions.clone()
+        if pol != "random":  # the random stream is keyed on the launch counter t, same for both here
+            assert torch.equal(standalone, applied)
+        else:
+            assert torch.equal(standalone, applied)
+        env.load_state(snap)
