@@ -78,13 +78,15 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     p.pairs_per_env = h->A * p.R;
     p.lut_entries = obs_dtype == CC_OBS_NONE ? 0 : h->epw * p.pairs_per_env;
     p.stage_pairs = obs_dtype == CC_OBS_NONE ? 0 : round_up(3 + h->epw * 2 * h->A, 8);
-    p.bitmap_words = needs_bitmap ? ((c.width + 1) * (c.height + 1) + 31) / 32 : 0;
+    p.walk_words = ((c.width + 3) * (c.height + 3) + 31) / 32;
     const int pair_bytes = obs_dtype == CC_OBS_FP32 ? 8 : 2;
     int off = round_up(p.lut_entries * 2, 16);
+    p.off_walk = off;
+    off += round_up(p.walk_words * 4, 16);
     p.off_stage = off;
     off += round_up(ccb::kWarpsPerCta * p.stage_pairs * pair_bytes, 16);
     p.off_bitmap = off;
-    off += round_up(ccb::kWarpsPerCta * h->epw * p.bitmap_words * 4, 16);
+    off += needs_bitmap ? round_up(ccb::kWarpsPerCta * h->epw * p.walk_words * 4, 16) : 0;
     p.off_red = off;
     p.n_groups = (h->n_envs + h->epw - 1) / h->epw;
 }

@@ -55,8 +55,8 @@ struct KParams {
     int pairs_per_env;   // A * R
     int lut_entries;     // EPW * A * R
     int stage_pairs;     // 3 + EPW * 2A (per warp)
-    int bitmap_words;    // per env: ceil((W+1)(H+1)/32); 0 when no on-device policy can run
-    int off_stage, off_bitmap, off_red;
+    int walk_words;      // words of one padded-lattice bitmap: ceil((W+3)(H+3)/32)
+    int off_walk, off_stage, off_bitmap, off_red;
     long long n_groups;
 };
 
@@ -157,43 +157,44 @@ struct Tile {
 };
 
 // ---------------------------------------------------------------------------------------------
-// LUT: output pair index within the warp's chunk -> pair index in the warp's stage.
+// Observation expansion.
 // Row i of an env is  [P_i, K1, K2, S_0a, S_0b, S_1a, S_1b, ...] with S_ia,S_ib replaced by M
-// (observations.py:62-94), in pair units: P_i=(x_i,y_i) K1=(DC,D) K2=(DL,DR) S_ja=(x_j,y_j)
-// S_jb=(type_j,active_j) M=(-1,-1).  Stage: [K1, K2, M, then per tile 2A pairs S_*].
+// (observations.py:62-94), in PAIR units: P_i=(x_i,y_i) K1=(DC,D) K2=(DL,DR) S_ja=(x_j,y_j)
+// S_jb=(type_j,active_j) M=(-1,-1).  A warp stages [K1, K2, M, then per tile 2A pairs S_*] in
+// shared memory and gathers output pairs from there.  gather_index() maps a pair of the warp's
+// output chunk to its stage pair; it is loop-invariant, so it is evaluated once per kernel:
+// into per-lane registers when the chunk is small (A <= 13), else into a shared-memory LUT.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void build_lut(const KParams &p, uint16_t *lut) {
+__device__ __forceinline__ int gather_index(const KParams &p, int P) {
     const int A = p.A, R = p.R, ppe = p.pairs_per_env;
-    for (int P = threadIdx.x; P < p.lut_entries; P += blockDim.x) {
-        int tile = P / ppe, q0 = P - tile * ppe;
-        int i = q0 / R, q = q0 - i * R;
-        int base = 3 + tile * 2 * A;
-        int v;
-        if (q == 0) v = base + 2 * i;
-        else if (q == 1) v = 0;
-        else if (q == 2) v = 1;
-        else { int j = (q - 3) >> 1, h = (q - 3) & 1; v = (j == i) ? 2 : base + 2 * j + h; }
-        lut[P] = (uint16_t)v;
-    }
+    int tile = P / ppe, q0 = P - tile * ppe;
+    int i = q0 / R, q = q0 - i * R;
+    int base = 3 + tile * 2 * A;
+    if (q == 0) return base + 2 * i;
+    if (q == 1) return 0;
+    if (q == 2) return 1;
+    int j = (q - 3) >> 1, h = (q - 3) & 1;
+    return (j == i) ? 2 : base + 2 * j + h;
 }
 
-// Expand the staged table into observation rows: `count` pairs starting at global pair index
-// `gp0` of the obs tensor, written as 16-byte vectors wherever a whole vector lies inside the
-// range (always, except at the two ends of an odd-sized / unaligned chunk).
+// generic path: `count` pairs starting at global pair index gp0, 16-byte vectors wherever a whole
+// vector lies inside the range (everywhere except the ends of an unaligned / odd-sized chunk)
 template <typename T>
-__device__ __forceinline__ void emit_obs(T *obs, long long gp0, int count, const uint16_t *lut,
-                                         const typename PairOf<T>::type *stage, int lane) {
+__device__ __forceinline__ void emit_obs_lut(T *obs, long long gp0, int count, const uint16_t *lut,
+                                             const typename PairOf<T>::type *stage, int lane) {
     using P2 = typename PairOf<T>::type;
     constexpr int PPV = 16 / (int)sizeof(P2);  // pairs per 16-byte vector: 2 (fp32) or 8 (int8)
-    P2 *out = reinterpret_cast<P2 *>(obs);
-    const long long v_first = gp0 / PPV, v_last = (gp0 + count - 1) / PPV;
-    for (long long v = v_first + lane; v <= v_last; v += 32) {
-        const int p0 = (int)(v * PPV - gp0);  // chunk-local index of the vector's first pair
+    const long long v_first = gp0 / PPV;
+    const int head = (int)(gp0 - v_first * PPV);            // pairs of the first vector before the chunk
+    const int nvec = (head + count + PPV - 1) / PPV;
+    P2 *out = reinterpret_cast<P2 *>(obs) + v_first * PPV;  // vector-aligned base
+    for (int v = lane; v < nvec; v += 32) {
+        const int p0 = v * PPV - head;
         if (p0 >= 0 && p0 + PPV <= count) {
             union { uint4 u; P2 e[PPV]; } pk;
 #pragma unroll
             for (int e = 0; e < PPV; ++e) pk.e[e] = stage[lut[p0 + e]];
-            __stcs(reinterpret_cast<uint4 *>(out + v * PPV), pk.u);
+            __stcs(reinterpret_cast<uint4 *>(out) + v, pk.u);
         } else {
 #pragma unroll
             for (int e = 0; e < PPV; ++e)
@@ -201,6 +202,9 @@ __device__ __forceinline__ void emit_obs(T *obs, long long gp0, int count, const
         }
     }
 }
+
+constexpr int kDescRegs = 12;        // registers of cached gather descriptors per lane
+constexpr int kDescPairs = 32 * kDescRegs * 2;  // = 768 pairs per warp chunk
 
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
@@ -211,23 +215,55 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
     using OT = typename std::conditional<OBS == CC_OBS_FP32, float, int8_t>::type;
     using P2 = typename PairOf<OT>::type;
     constexpr int EPW = TL_::EPW;
+    constexpr int PPV = 16 / (int)sizeof(P2);
+    constexpr bool kHasObs = OBS != CC_OBS_NONE;
+    constexpr bool kCanCache = kHasObs && LPE <= 16;
+    constexpr bool kHasPolicy = MODE == kModeStep || MODE == kModePolicy;
+    constexpr bool kMoves = MODE == kModeStep;
     extern __shared__ __align__(16) unsigned char smem[];
 
     const TL_ T;
     const int warp = threadIdx.x >> 5;
     const int A = p.A;
     uint16_t *lut = reinterpret_cast<uint16_t *>(smem);
-    P2 *stage = reinterpret_cast<P2 *>(smem + p.off_stage) + (size_t)warp * p.stage_pairs;
-    unsigned *bitmap = reinterpret_cast<unsigned *>(smem + p.off_bitmap) + ((size_t)warp * EPW + T.tile) * p.bitmap_words;
+    unsigned *walk = reinterpret_cast<unsigned *>(smem + p.off_walk);
+    P2 *stage = reinterpret_cast<P2 *>(smem + p.off_stage) + warp * p.stage_pairs;
+    unsigned *blocked = reinterpret_cast<unsigned *>(smem + p.off_bitmap) + (warp * EPW + T.tile) * p.walk_words;
+    const int PW = p.W + 3;  // padded lattice: x in [-1, W+1] -> column x+1
 
-    if (OBS != CC_OBS_NONE) {
-        build_lut(p, lut);
+    // whole-chunk fast path of the observation gather: descriptors live in registers
+    const int chunk_pairs = EPW * p.pairs_per_env;
+    const bool cached = kCanCache && chunk_pairs <= kDescPairs && (chunk_pairs % PPV) == 0;
+    unsigned desc[kCanCache ? kDescRegs : 1];
+    if (kHasObs) {
+        if (cached) {
+            // fp32: one register = the two pairs of one 16-byte vector; int8: four registers = 8 pairs
+            constexpr int RPV = PPV / 2;
+#pragma unroll
+            for (int r = 0; r < (kCanCache ? kDescRegs : 1); ++r) {
+                const int v = T.lane + 32 * (r / RPV);
+                const int P = v * PPV + 2 * (r % RPV);
+                desc[r] = (P + 1 < chunk_pairs) ? ((unsigned)gather_index(p, P) | ((unsigned)gather_index(p, P + 1) << 16)) : 0u;
+            }
+        } else {
+            for (int P = threadIdx.x; P < p.lut_entries; P += blockDim.x) lut[P] = (uint16_t)gather_index(p, P);
+        }
         if (T.lane == 0) { stage[0] = mk_pair<OT>(p.DC, p.D); stage[1] = mk_pair<OT>(p.DL, p.DR); stage[2] = mk_pair<OT>(-1, -1); }
-        __syncthreads();
     }
+    // static map of walkable lattice points (collectivecrossing.py:509-534), one bit per point of
+    // the padded lattice; the padding ring is not walkable, so neighbour tests need no bounds check
+    for (int w = threadIdx.x; w < p.walk_words; w += blockDim.x) {
+        unsigned bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int idx = w * 32 + b, yy = idx / PW - 1, xx = idx - (yy + 1) * PW - 1;
+            bits |= valid_position(p, xx, yy) && yy <= p.H + 1 ? (1u << b) : 0u;
+        }
+        walk[w] = bits;
+    }
+    __syncthreads();
 
     // per-thread statistics (only tile leaders contribute)
-    long long st_steps = 0, st_episodes = 0, st_term = 0, st_trunc = 0, st_arrivals = 0, st_eplen = 0;
+    unsigned st_steps = 0, st_episodes = 0, st_term = 0, st_trunc = 0, st_arrivals = 0, st_eplen = 0;
     double st_epret = 0.0, st_rsum = 0.0;
     int errbits = 0;
 
@@ -235,51 +271,66 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
     bool avalid[APL];
 #pragma unroll
     for (int k = 0; k < APL; ++k) { aidx[k] = T.li + k * LPE; avalid[k] = aidx[k] < A; }
+    const unsigned tile_bits = TL_::MASK << T.tshift;
 
     const long long total_warps = (long long)gridDim.x * kWarpsPerCta;
     for (long long g = (long long)blockIdx.x * kWarpsPerCta + warp; g < p.n_groups; g += total_warps) {
-        const long long n = g * EPW + T.tile;
-        const bool env_ok = n < p.n_envs;
-        const unsigned long long genv = p.genv_offset + (unsigned long long)n;
-        const long long row = n * A;
+        const long long n0 = g * EPW;
+        const long long rem = p.n_envs - n0;
+        const int envs_here = rem < EPW ? (int)rem : EPW;
+        const bool env_ok = T.tile < envs_here;
+        const unsigned long long genv = p.genv_offset + (unsigned long long)(n0 + T.tile);
+        const long long row0 = n0 * A;             // first agent slot of the group
+        int off[APL];                               // this lane's agent slots relative to row0
+#pragma unroll
+        for (int k = 0; k < APL; ++k) off[k] = T.tile * A + aidx[k];
 
         // ---- load the env's record (one contiguous run of bytes per array per warp) ----------
         unsigned pos[APL];
         unsigned fl[APL];
         int action[APL];
+        {
+            const int8_t *gx = p.x + row0, *gy = p.y + row0;
+            const uint8_t *gf = p.flags + row0;
 #pragma unroll
-        for (int k = 0; k < APL; ++k) {
-            pos[k] = 0; fl[k] = 0; action[k] = CC_ACT_WAIT;
-            if (env_ok && avalid[k]) {
-                pos[k] = pack_pos(p.x[row + aidx[k]], p.y[row + aidx[k]]);
-                fl[k] = p.flags[row + aidx[k]];
-                if (MODE == kModeStep && p.policy == CC_POLICY_EXTERNAL) action[k] = p.actions[row + aidx[k]];
+            for (int k = 0; k < APL; ++k) {
+                pos[k] = 0; fl[k] = 0; action[k] = CC_ACT_WAIT;
+                if (env_ok && avalid[k]) {
+                    pos[k] = pack_pos(gx[off[k]], gy[off[k]]);
+                    fl[k] = gf[off[k]];
+                    if (kMoves && p.policy == CC_POLICY_EXTERNAL) action[k] = (p.actions + row0)[off[k]];
+                }
             }
         }
-        int step = env_ok ? p.step[n] : 0;
-        float ep_ret = (env_ok && MODE == kModeStep) ? p.ep_ret[n] : 0.f;
+        int step = env_ok ? (p.step + n0)[T.tile] : 0;
+        float ep_ret = (env_ok && kMoves) ? (p.ep_ret + n0)[T.tile] : 0.f;
+
+        // padded-lattice cell of every owned agent (centre clamped into the lattice: set_state
+        // promises in-lattice positions, the clamp only keeps shared-memory reads in bounds)
+        int cell[APL];
+        if (kHasPolicy) {
+#pragma unroll
+            for (int k = 0; k < APL; ++k) {
+                const int cx = min(max(pos_x(pos[k]), 0), p.W) + 1, cy = min(max(pos_y(pos[k]), 0), p.H) + 1;
+                cell[k] = cy * PW + cx;
+            }
+        }
 
         // ---- on-device policies (baseline_policies/*.py at randomness_factor 0) ---------------
-        if ((MODE == kModeStep || MODE == kModePolicy) && p.policy != CC_POLICY_EXTERNAL) {
+        bool geo_known = false;  // chosen moves already passed the geometric test
+        if (kHasPolicy && p.policy != CC_POLICY_EXTERNAL) {
             if (p.policy == CC_POLICY_RANDOM) {
 #pragma unroll
                 for (int k = 0; k < APL; ++k)
                     if (env_ok && avalid[k]) action[k] = bounded(draw(p, genv, kStreamAction, (unsigned)aidx[k]).v0, 5);
             } else {
-                // occupancy grid of ACTIVE agents in shared memory (collectivecrossing.py:536-541
-                // as a bit test; the asking agent's own cell is never a neighbour cell)
-                const int stride = p.W + 1;
-                for (int w = T.li; w < p.bitmap_words; w += LPE) bitmap[w] = 0u;
+                // blocked = walls | cells held by ACTIVE agents (collectivecrossing.py:345-369 as
+                // one bit test; the asking agent's own cell is never one of its neighbour cells)
+                for (int w = T.li; w < p.walk_words; w += LPE) blocked[w] = ~walk[w];
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < APL; ++k)
-                    if (env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE)) {
-                        int x = pos_x(pos[k]), y = pos_y(pos[k]);
-                        if ((unsigned)x <= (unsigned)p.W && (unsigned)y <= (unsigned)p.H) {
-                            int b = y * stride + x;
-                            atomicOr(&bitmap[b >> 5], 1u << (b & 31));
-                        }
-                    }
+                    if (env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE)) atomicOr(&blocked[cell[k] >> 5], 1u << (cell[k] & 31));
                 __syncwarp();
                 // waiting_policy.py:118-131: some exiting agent that is not done has not arrived
                 bool pending = false;
@@ -287,71 +338,70 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
                 for (int k = 0; k < APL; ++k)
                     pending |= env_ok && avalid[k] && aidx[k] >= p.B && !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED)) &&
                                pos_y(pos[k]) != p.YE;
-                const bool exiting_pending = T.tballot(pending) != 0u;
+                const bool exiting_pending = p.policy == CC_POLICY_WAITING && (__ballot_sync(kFull, pending) & tile_bits) != 0u;
 #pragma unroll
                 for (int k = 0; k < APL; ++k) {
                     int a = CC_ACT_WAIT;
-                    const bool asks = env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE) && !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED));
+                    const bool asks = env_ok && avalid[k] && (fl[k] & 7u) == CC_F_ACTIVE;  // active, not done
                     if (asks) {
                         const int x = pos_x(pos[k]), y = pos_y(pos[k]);
                         const bool boarding = aidx[k] < p.B;
-                        const bool waits = p.policy == CC_POLICY_WAITING && boarding && !in_tram_area(p, x, y) && exiting_pending;
+                        const bool waits = exiting_pending && boarding && !in_tram_area(p, x, y);
                         if (!waits) {
                             // validity of the four moves (greedy_policy.py:238-264 -> _is_move_valid)
-                            unsigned vmask = 0;
-#pragma unroll
-                            for (int m = 0; m < 4; ++m) {
-                                int nx = x + act_dx(m), ny = y + act_dy(m);
-                                bool ok = valid_position(p, nx, ny);
-                                if (ok) { int b = ny * stride + nx; ok = !((bitmap[b >> 5] >> (b & 31)) & 1u); }
-                                vmask |= ok ? (1u << m) : 0u;
-                            }
-                            // greedy_policy.py:90-161 _calculate_direction (+ :163-236)
-                            int dx = 0, dy = 0;
+                            const int c = cell[k];
+                            auto is_free = [&](int idx) { return ((blocked[idx >> 5] >> (idx & 31)) & 1u) ^ 1u; };
+                            const unsigned vmask = is_free(c + 1) | (is_free(c + PW) << 1) | (is_free(c - 1) << 2) | (is_free(c - PW) << 3);
+                            // greedy_policy.py:90-161 _calculate_direction (+ :163-236); the fallback
+                            // lists (:311-449) are 4 nibbles, first choice lowest
                             const int D = p.D, dc = p.DC;
-                            auto sgn = [](int v) { return (v > 0) - (v < 0); };
-                            unsigned pref;  // fallback list, 4 nibbles, first choice lowest (greedy_policy.py:311-449)
+                            const int toward_dc = x < dc ? CC_ACT_RIGHT : CC_ACT_LEFT;
+                            int want;
+                            unsigned pref;
                             if (boarding) {
                                 if (y < D) {
-                                    if (y == D - 1) { if (x == dc) dy = 1; else dx = sgn(dc - x); }
-                                    else dy = 1;
+                                    want = (y == D - 1 && x != dc) ? toward_dc : CC_ACT_UP;
                                     pref = (x < dc) ? 0x3210u : (x > dc) ? 0x3012u : 0x3201u;  // RULD | LURD | URLD
-                                } else { dy = sgn(p.YB - y); pref = 0x3201u; }
+                                } else {
+                                    want = y < p.YB ? CC_ACT_UP : y > p.YB ? CC_ACT_DOWN : CC_ACT_WAIT;
+                                    pref = 0x3201u;
+                                }
                             } else {
                                 if (y > D) {
-                                    if (y == D + 1) { if (x == dc) dy = -1; else dx = sgn(dc - x); }
-                                    else dy = -1;
+                                    want = (y == D + 1 && x != dc) ? toward_dc : CC_ACT_DOWN;
                                     pref = (x < dc) ? 0x1230u : (x > dc) ? 0x1032u : 0x1203u;  // RDLU | LDRU | DRLU
-                                } else { dy = sgn(p.YE - y); pref = 0x1203u; }
+                                } else {
+                                    want = y > p.YE ? CC_ACT_DOWN : y < p.YE ? CC_ACT_UP : CC_ACT_WAIT;
+                                    pref = 0x1203u;
+                                }
                             }
-                            int want = dx == 1 ? CC_ACT_RIGHT : dx == -1 ? CC_ACT_LEFT : dy == 1 ? CC_ACT_UP : dy == -1 ? CC_ACT_DOWN : CC_ACT_WAIT;
                             if (want == CC_ACT_WAIT || ((vmask >> want) & 1u)) a = want;
                             else {
-                                a = CC_ACT_WAIT;
 #pragma unroll
-                                for (int c = 3; c >= 0; --c) { int cand = (pref >> (4 * c)) & 15; if ((vmask >> cand) & 1u) a = cand; }
+                                for (int cnd = 3; cnd >= 0; --cnd) { const int cand = (pref >> (4 * cnd)) & 15; if ((vmask >> cand) & 1u) a = cand; }
                             }
                         }
                     }
                     action[k] = a;
                 }
+                geo_known = true;
                 __syncwarp();
             }
         }
         if (MODE == kModePolicy) {
 #pragma unroll
             for (int k = 0; k < APL; ++k)
-                if (env_ok && avalid[k]) p.actions_out[row + aidx[k]] = (int8_t)action[k];
+                if (env_ok && avalid[k]) (p.actions_out + row0)[off[k]] = (int8_t)action[k];
             continue;
         }
 
         bool need_reset = false;
         unsigned eflags = 0;
-        if (MODE == kModeStep) {
+        if (kMoves) {
             if (p.actions_out) {
 #pragma unroll
                 for (int k = 0; k < APL; ++k)
-                    if (env_ok && avalid[k]) p.actions_out[row + aidx[k]] = (int8_t)action[k];
+                    if (env_ok && avalid[k]) (p.actions_out + row0)[off[k]] = (int8_t)action[k];
             }
             // ---- collectivecrossing.py:188 ---------------------------------------------------
             step += 1;
@@ -360,32 +410,46 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
             for (int k = 0; k < APL; ++k) alive_prev[k] = avalid[k] && !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED));
 
             // ---- collectivecrossing.py:197-202: ordered moves -------------------------------
+            // cmp[k] = packed position of an ACTIVE agent, else a sentinel no target can equal;
+            // a request is the packed target cell, or kNoMove.  A mover's target never equals its
+            // own cell, so the occupancy ballot (:536-541) needs no self-exclusion.
+            constexpr unsigned kNoMove = 0xFFFFFFFEu, kGhost = 0xFFFFFFFFu;
+            unsigned cmp[APL];
+#pragma unroll
+            for (int k = 0; k < APL; ++k) cmp[k] = (env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE)) ? pos[k] : kGhost;
+            auto make_request = [&](unsigned my_pos, int my_cell, int my_act, unsigned my_cmp) -> unsigned {
+                if (my_cmp == kGhost || (unsigned)my_act >= 4u) return kNoMove;        // :398, wait
+                if (!geo_known) {                                                       // :509-534 via the static map
+                    const int t = my_cell + act_dx(my_act) + PW * act_dy(my_act);
+                    if (!((walk[t >> 5] >> (t & 31)) & 1u)) return kNoMove;
+                }
+                return pack_pos(pos_x(my_pos) + act_dx(my_act), pos_y(my_pos) + act_dy(my_act));
+            };
             if (p.order == nullptr) {
                 // every agent has an entry: :707-711 applies to all of them
-#pragma unroll
-                for (int k = 0; k < APL; ++k)
-                    if (env_ok && avalid[k] && (unsigned)action[k] > 4u) errbits |= kErrInvalidAction;
                 unsigned req[APL];
 #pragma unroll
-                for (int k = 0; k < APL; ++k) req[k] = move_request(p, pos[k], action[k], env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE));
+                for (int k = 0; k < APL; ++k) {
+                    if (env_ok && avalid[k] && (unsigned)action[k] > 4u) errbits |= kErrInvalidAction;
+                    req[k] = make_request(pos[k], cell[k], action[k], cmp[k]);
+                }
 #pragma unroll
                 for (int s = 0; s < APL; ++s) {
                     const int lim = min(LPE, A - s * LPE);
 #pragma unroll 8
                     for (int l = 0; l < lim; ++l) {
                         const unsigned rq = T.tshfl(req[s], l);
-                        bool hit = false;  // :536-541 another ACTIVE agent on the target cell
+                        bool hit = false;
 #pragma unroll
-                        for (int k = 0; k < APL; ++k)
-                            hit |= avalid[k] && (fl[k] & CC_F_ACTIVE) && pos[k] == (rq & 0xffffu) && !(k == s && T.li == l);
-                        const unsigned occ = T.tballot(hit);
-                        if (T.li == l && (rq >> 31) && !occ) pos[s] = rq & 0xffffu;  // :406-408
+                        for (int k = 0; k < APL; ++k) hit |= cmp[k] == rq;
+                        const unsigned occ = __ballot_sync(kFull, hit) & tile_bits;
+                        if (T.li == l && rq != kNoMove && !occ) { pos[s] = rq; cmp[s] = rq; }   // :406-408
                     }
                 }
             } else {
                 int ord[APL];
 #pragma unroll
-                for (int k = 0; k < APL; ++k) ord[k] = (env_ok && avalid[k]) ? (int)p.order[row + aidx[k]] : -1;
+                for (int k = 0; k < APL; ++k) ord[k] = (env_ok && avalid[k]) ? (int)(p.order + row0)[off[k]] : -1;
                 bool stop = !env_ok;
                 for (int k = 0; k < A; ++k) {
                     const int oi = (int)T.tshfl((unsigned)picki<APL>(ord, k >> TL_::LOG), k & (LPE - 1));
@@ -394,20 +458,20 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
                     if (live && oi >= A) { errbits |= kErrInvalidAction; live = false; }  // :701-705
                     const int ol = oi & (LPE - 1), os = oi >> TL_::LOG;
                     const int my_act = picki<APL>(action, os);
-                    const unsigned my_pos = pick<APL>(pos, os);
-                    const unsigned my_fl = pick<APL>(fl, os);
+                    const unsigned my_pos = pick<APL>(pos, os), my_cmp = pick<APL>(cmp, os);
                     const bool owner = live && T.li == ol;
                     if (owner && (unsigned)my_act > 4u) errbits |= kErrInvalidAction;   // :707-711
-                    unsigned rq = T.tshfl(move_request(p, my_pos, my_act, (my_fl & CC_F_ACTIVE) != 0), ol);
-                    if (!live) rq = 0;
+                    // the cell is recomputed: an agent listed twice has moved since the top of the step
+                    const int my_cell = (min(max(pos_y(my_pos), 0), p.H) + 1) * PW + min(max(pos_x(my_pos), 0), p.W) + 1;
+                    unsigned rq = T.tshfl(make_request(my_pos, my_cell, my_act, my_cmp), ol);
+                    if (!live) rq = kNoMove;
                     bool hit = false;
 #pragma unroll
-                    for (int s = 0; s < APL; ++s)
-                        hit |= avalid[s] && (fl[s] & CC_F_ACTIVE) && pos[s] == (rq & 0xffffu) && !(s == os && T.li == ol);
-                    const unsigned occ = T.tballot(hit);
-                    if (owner && (rq >> 31) && !occ) {
+                    for (int s = 0; s < APL; ++s) hit |= cmp[s] == rq;
+                    const unsigned occ = __ballot_sync(kFull, hit) & tile_bits;
+                    if (owner && rq != kNoMove && !occ) {
 #pragma unroll
-                        for (int s = 0; s < APL; ++s) if (s == os) pos[s] = rq & 0xffffu;
+                        for (int s = 0; s < APL; ++s) if (s == os) { pos[s] = rq; cmp[s] = rq; }
                     }
                 }
             }
@@ -415,17 +479,17 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
             // ---- :210-212 deactivate arrivals; rewards; terminated; truncated --------------
             bool arr[APL];
             int n_arrived_now = 0;
-            bool lane_all_arr = true;
+            bool lane_not_arr = false;
 #pragma unroll
             for (int k = 0; k < APL; ++k) {
                 const int dest = aidx[k] < p.B ? p.YB : p.YE;          // :663-683 (y only)
                 arr[k] = avalid[k] && pos_y(pos[k]) == dest;
                 const bool newly = arr[k] && (fl[k] & CC_F_ACTIVE);
                 if (newly) fl[k] &= ~(unsigned)CC_F_ACTIVE;            // types.py:46-51
-                n_arrived_now += __popc(T.tballot(env_ok && newly));
-                lane_all_arr = lane_all_arr && (arr[k] || !avalid[k]);
+                n_arrived_now += __popc(__ballot_sync(kFull, env_ok && newly) & tile_bits);
+                lane_not_arr = lane_not_arr || (avalid[k] && !arr[k]);
             }
-            const bool all_arrived = T.tballot(!lane_all_arr) == 0u;
+            const bool all_arrived = (__ballot_sync(kFull, lane_not_arr) & tile_bits) == 0u;
             const bool over_limit = step >= p.max_steps;                // truncateds.py:61
             bool lane_alive = false;
             float rsum_lane = 0.f;
@@ -469,7 +533,7 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
                 oflag[k] = (fl[k] & 7u) | (alive_prev[k] ? CC_O_ALIVE_PREV : 0u) | (tval ? CC_O_TERM_VALUE : 0u) |
                            (cval ? CC_O_TRUNC_VALUE : 0u) | (present ? CC_O_OBS_PRESENT : 0u);
             }
-            const bool any_alive = T.tballot(lane_alive) != 0u;
+            const bool any_alive = (__ballot_sync(kFull, lane_alive) & tile_bits) != 0u;
             const bool term_all = all_arrived;                          // :256 (terminateds holds every agent)
             const bool trunc_all = any_alive && over_limit;             // :257
             // reward sum: balanced tree over the tile's lanes (fixed association order; the oracle
@@ -485,14 +549,13 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
 #pragma unroll
             for (int k = 0; k < APL; ++k)
                 if (env_ok && avalid[k]) {
-                    const long long o = row + aidx[k];
-                    if (p.reward_f64) reinterpret_cast<double *>(p.reward)[o] = rew[k];
-                    else reinterpret_cast<float *>(p.reward)[o] = (float)rew[k];
-                    p.agent_flags[o] = (uint8_t)oflag[k];
+                    if (p.reward_f64) (reinterpret_cast<double *>(p.reward) + row0)[off[k]] = rew[k];
+                    else (reinterpret_cast<float *>(p.reward) + row0)[off[k]] = (float)rew[k];
+                    (p.agent_flags + row0)[off[k]] = (uint8_t)oflag[k];
                     if (p.agent_info) {                                 // :248-254
                         const int x = pos_x(pos[k]), y = pos_y(pos[k]);
-                        p.agent_info[o] = (uint8_t)((in_tram_area(p, x, y) ? CC_I_IN_TRAM_AREA : 0) | (at_tram_door(p, x, y) ? CC_I_AT_DOOR : 0) |
-                                                    ((fl[k] & CC_F_ACTIVE) ? CC_I_ACTIVE : 0) | (arr[k] ? CC_I_AT_DESTINATION : 0));
+                        (p.agent_info + row0)[off[k]] = (uint8_t)((in_tram_area(p, x, y) ? CC_I_IN_TRAM_AREA : 0) | (at_tram_door(p, x, y) ? CC_I_AT_DOOR : 0) |
+                                                                  ((fl[k] & CC_F_ACTIVE) ? CC_I_ACTIVE : 0) | (arr[k] ? CC_I_AT_DESTINATION : 0));
                     }
                 }
             if (env_ok && T.li == 0) {
@@ -507,7 +570,7 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
             need_reset = env_ok && done && p.auto_reset;
             if (need_reset) { eflags |= CC_E_WAS_RESET; ep_ret = 0.f; }
         }
-        if (MODE == kModeReset) need_reset = env_ok && (p.mask == nullptr || p.mask[n] != 0);
+        if (MODE == kModeReset) need_reset = env_ok && (p.mask == nullptr || (p.mask + n0)[T.tile] != 0);
 
         // ---- collectivecrossing.py:91-150 reset(): rejection-sampled placement ---------------
         // Agent i's k-th candidate is Philox(seed; genv, t, RESET, i<<16|k); it takes the first
@@ -554,7 +617,7 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
                     bool hit = false;
 #pragma unroll
                     for (int s = 0; s < APL; ++s) hit |= placed[s] && pos[s] == (rq & 0xffffu);
-                    const unsigned occ = T.tballot(hit);
+                    const unsigned occ = __ballot_sync(kFull, hit) & tile_bits;
                     if (act_tile && (rq >> 31)) {
                         if (!occ || forced) {
                             if (T.li == ol) {
@@ -590,19 +653,19 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
 #pragma unroll
             for (int k = 0; k < APL; ++k)
                 if (wr && avalid[k]) {
-                    p.x[row + aidx[k]] = (int8_t)pos_x(pos[k]);
-                    p.y[row + aidx[k]] = (int8_t)pos_y(pos[k]);
-                    p.flags[row + aidx[k]] = (uint8_t)(fl[k] & 7u);
+                    (p.x + row0)[off[k]] = (int8_t)pos_x(pos[k]);
+                    (p.y + row0)[off[k]] = (int8_t)pos_y(pos[k]);
+                    (p.flags + row0)[off[k]] = (uint8_t)(fl[k] & 7u);
                 }
             if (wr && T.li == 0) {
-                p.step[n] = step;
-                p.ep_ret[n] = ep_ret;
-                if (MODE == kModeStep) p.env_flags[n] = (uint8_t)eflags;
+                (p.step + n0)[T.tile] = step;
+                (p.ep_ret + n0)[T.tile] = ep_ret;
+                if (MODE == kModeStep) (p.env_flags + n0)[T.tile] = (uint8_t)eflags;
             }
         }
 
         // ---- observations.py:43-94 from the post-step (post-reset) state ------------------------
-        if (OBS != CC_OBS_NONE && p.obs != nullptr) {
+        if (kHasObs && p.obs != nullptr) {
             P2 *tstage = stage + 3 + T.tile * 2 * A;
 #pragma unroll
             for (int k = 0; k < APL; ++k)
@@ -611,19 +674,58 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
                     tstage[2 * aidx[k] + 1] = mk_pair<OT>(aidx[k] < p.B ? 0 : 1, (fl[k] & CC_F_ACTIVE) ? 1 : 0);
                 }
             __syncwarp();
-            const long long n0 = g * EPW;
+            OT *obs = reinterpret_cast<OT *>(p.obs);
+            const long long gp0 = n0 * (long long)p.pairs_per_env;
             if (MODE == kModeReset) {
                 // only the envs that were reset get their rows rewritten
                 const unsigned tiles = __ballot_sync(kFull, need_reset);
+                if (!cached) {
 #pragma unroll
-                for (int e = 0; e < EPW; ++e)
-                    if ((tiles >> (e * LPE)) & 1u)
-                        emit_obs<OT>(reinterpret_cast<OT *>(p.obs), (n0 + e) * (long long)p.pairs_per_env, p.pairs_per_env,
-                                     lut + e * p.pairs_per_env, stage, T.lane);
+                    for (int e = 0; e < EPW; ++e)
+                        if ((tiles >> (e * LPE)) & 1u)
+                            emit_obs_lut<OT>(obs, gp0 + (long long)e * p.pairs_per_env, p.pairs_per_env, lut + e * p.pairs_per_env, stage, T.lane);
+                }
+                if (kCanCache && cached) {
+                    // descriptors exist per whole chunk: store only the pairs of reset envs
+                    P2 *out = reinterpret_cast<P2 *>(obs) + gp0;
+                    constexpr int RPV = PPV / 2;
+#pragma unroll
+                    for (int r = 0; r < kDescRegs; ++r) {
+                        const int P = (T.lane + 32 * (r / RPV)) * PPV + 2 * (r % RPV);
+                        if (P + 1 < envs_here * p.pairs_per_env) {
+                            const int e0 = P / p.pairs_per_env, e1 = (P + 1) / p.pairs_per_env;
+                            if ((tiles >> (e0 * LPE)) & 1u) out[P] = stage[desc[r] & 0xffffu];
+                            if ((tiles >> (e1 * LPE)) & 1u) out[P + 1] = stage[desc[r] >> 16];
+                        }
+                    }
+                }
+            } else if (kCanCache && cached && envs_here == EPW) {
+                // whole, vector-aligned chunk: gather through the register-resident descriptors
+                uint4 *outv = reinterpret_cast<uint4 *>(reinterpret_cast<P2 *>(obs) + gp0) + T.lane;
+                const int nvec = chunk_pairs / PPV;
+                constexpr int RPV = PPV / 2;
+#pragma unroll
+                for (int j = 0; j < kDescRegs / RPV; ++j) {
+                    if (T.lane + 32 * j < nvec) {
+                        union { uint4 u; P2 e[PPV]; } pk;
+#pragma unroll
+                        for (int h = 0; h < RPV; ++h) {
+                            const unsigned d = desc[j * RPV + h];
+                            pk.e[2 * h] = stage[d & 0xffffu];
+                            pk.e[2 * h + 1] = stage[d >> 16];
+                        }
+                        __stcs(outv + 32 * j, pk.u);
+                    }
+                }
             } else {
-                const long long rem = p.n_envs - n0;
-                const int envs_here = rem < EPW ? (int)rem : EPW;
-                emit_obs<OT>(reinterpret_cast<OT *>(p.obs), n0 * (long long)p.pairs_per_env, envs_here * p.pairs_per_env, lut, stage, T.lane);
+                if (cached) {
+                    // ragged last group of a run that otherwise uses the descriptors: the LUT was
+                    // not built, gather with the index function directly (once per launch at most)
+                    P2 *out = reinterpret_cast<P2 *>(obs) + gp0;
+                    for (int P = T.lane; P < envs_here * p.pairs_per_env; P += 32) out[P] = stage[gather_index(p, P)];
+                } else {
+                    emit_obs_lut<OT>(obs, gp0, envs_here * p.pairs_per_env, lut, stage, T.lane);
+                }
             }
             __syncwarp();
         }
@@ -632,27 +734,33 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
     // ---- statistics: warp shuffle -> shared memory -> one atomic per slot per CTA -----------------
     if (MODE == kModeStep) {
         unsigned long long *red = reinterpret_cast<unsigned long long *>(smem + p.off_red);
-        long long iv[6] = {st_steps, st_episodes, st_term, st_trunc, st_arrivals, st_eplen};
+        unsigned iv[6] = {st_steps, st_episodes, st_term, st_trunc, st_arrivals, st_eplen};
         double dv[2] = {st_epret, st_rsum};
+        unsigned long long iv64[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            // counts per lane fit 32 bits; widen before the cross-lane sum
+            unsigned long long v = iv[i];
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) v += __shfl_xor_sync(kFull, v, w);
+            iv64[i] = v;
+        }
 #pragma unroll
         for (int w = 16; w >= 1; w >>= 1) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) iv[i] += __shfl_xor_sync(kFull, iv[i], w);
-#pragma unroll
             for (int i = 0; i < 2; ++i) dv[i] += __shfl_xor_sync(kFull, dv[i], w);
         }
-        __syncthreads();  // smem may still be read as LUT / stage by slower warps
         if (T.lane == 0) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) red[warp * kStCount + i] = (unsigned long long)iv[i];
+            for (int i = 0; i < 6; ++i) red[warp * kStCount + i] = iv64[i];
 #pragma unroll
             for (int i = 0; i < 2; ++i) red[warp * kStCount + 6 + i] = (unsigned long long)__double_as_longlong(dv[i]);
         }
         __syncthreads();
         if (threadIdx.x < 6) {
-            long long s = 0;
-            for (int w = 0; w < kWarpsPerCta; ++w) s += (long long)red[w * kStCount + threadIdx.x];
-            if (s) atomicAdd(&p.stats[threadIdx.x], (unsigned long long)s);
+            unsigned long long s = 0;
+            for (int w = 0; w < kWarpsPerCta; ++w) s += red[w * kStCount + threadIdx.x];
+            if (s) atomicAdd(&p.stats[threadIdx.x], s);
         } else if (threadIdx.x < 8) {
             double s = 0.0;
             for (int w = 0; w < kWarpsPerCta; ++w) s += __longlong_as_double((long long)red[w * kStCount + threadIdx.x]);
