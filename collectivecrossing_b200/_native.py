@@ -5,13 +5,14 @@ the product raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 from . import _abi
 
 CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = CSRC / "libccb200.so"
+LIB_PATH = Path(os.environ.get("CCB200_LIB", CSRC / "libccb200.so"))  # override: A/B builds of the same ABI
 _lib = None
 
 

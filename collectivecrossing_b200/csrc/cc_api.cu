@@ -70,7 +70,7 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     p.DL = c.door_left; p.DR = c.door_right; p.DC = (c.door_left + c.door_right) / 2;
     p.YB = c.boarding_dest_y; p.YE = c.exiting_dest_y; p.B = c.num_boarding; p.A = h->A;
     p.max_steps = c.max_steps; p.reward_kind = c.reward_kind; p.terminated_kind = c.terminated_kind;
-    for (int i = 0; i < 4; ++i) p.rp[i] = c.reward_params[i];
+    for (int i = 0; i < 4; ++i) { p.rp[i] = c.reward_params[i]; p.rpf[i] = (float)c.reward_params[i]; }
     p.n_envs = h->n_envs; p.genv_offset = (unsigned long long)h->genv_offset; p.seed = h->seed; p.t = (unsigned)h->t;
     p.x = h->x; p.y = h->y; p.flags = h->flags; p.step = h->step; p.ep_ret = h->ep_ret;
     p.stats = h->stats; p.err = h->err;
@@ -88,9 +88,15 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     p.off_bitmap = off;
     off += needs_bitmap ? round_up(ccb::kWarpsPerCta * h->epw * p.walk_words * 4, 16) : 0;
     p.off_red = off;
+    off += ccb::kWarpsPerCta * ccb::kStCount * 8;
+    p.off_desc = off;
+    off += (obs_dtype != CC_OBS_NONE && h->lpe <= 16) ? ccb::kDescRegs * 4 * ccb::kThreads : 0;
+    p.off_rtab = off;
+    off += 2 * ccb::kRtabSize * 4;
+    p.smem_total = off;
     p.n_groups = (h->n_envs + h->epw - 1) / h->epw;
 }
-int smem_bytes(const KParams &p) { return p.off_red + ccb::kWarpsPerCta * ccb::kStCount * 8; }
+int smem_bytes(const KParams &p) { return p.smem_total; }
 
 template <int LPE, int APL, int OBS, int MODE>
 int launch_t(cc_handle *h, const KParams &p, cudaStream_t s) {

@@ -15,6 +15,10 @@
 
 #include "../../include/ccb200.h"
 
+#ifndef CCB_MIN_BLOCKS
+#define CCB_MIN_BLOCKS 5  // resident CTAs per SM the register allocator must allow (A/B in DESIGN.md §6)
+#endif
+
 namespace ccb {
 
 constexpr int kWarpsPerCta = 8;
@@ -56,8 +60,10 @@ struct KParams {
     int lut_entries;     // EPW * A * R
     int stage_pairs;     // 3 + EPW * 2A (per warp)
     int walk_words;      // words of one padded-lattice bitmap: ceil((W+3)(H+3)/32)
-    int off_walk, off_stage, off_bitmap, off_red;
+    int off_walk, off_stage, off_bitmap, off_red, off_desc, off_rtab;
+    float rpf[4];        // reward parameters rounded to float32 once
     long long n_groups;
+    int smem_total;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -205,12 +211,13 @@ __device__ __forceinline__ void emit_obs_lut(T *obs, long long gp0, int count, c
 
 constexpr int kDescRegs = 12;        // registers of cached gather descriptors per lane
 constexpr int kDescPairs = 32 * kDescRegs * 2;  // = 768 pairs per warp chunk
+constexpr int kRtabOff = 256, kRtabSize = 768;  // distance range of int8 coordinates: [-256, 511]
 
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
 template <int LPE, int APL, int OBS, int MODE>
-__global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kThreads, CCB_MIN_BLOCKS) cc_kernel(const __grid_constant__ KParams p) {
     using TL_ = Tile<LPE, APL>;
     using OT = typename std::conditional<OBS == CC_OBS_FP32, float, int8_t>::type;
     using P2 = typename PairOf<OT>::type;
@@ -231,24 +238,42 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
     unsigned *blocked = reinterpret_cast<unsigned *>(smem + p.off_bitmap) + (warp * EPW + T.tile) * p.walk_words;
     const int PW = p.W + 3;  // padded lattice: x in [-1, W+1] -> column x+1
 
-    // whole-chunk fast path of the observation gather: descriptors live in registers
+    // whole-chunk fast path of the observation gather: each lane's descriptors are loop-invariant;
+    // they live in shared memory as [kDescRegs/4][kThreads] uint4 (conflict-free LDS.128)
     const int chunk_pairs = EPW * p.pairs_per_env;
     const bool cached = kCanCache && chunk_pairs <= kDescPairs && (chunk_pairs % PPV) == 0;
-    unsigned desc[kCanCache ? kDescRegs : 1];
+    uint4 *desc_sm = reinterpret_cast<uint4 *>(smem + p.off_desc) + threadIdx.x;
+    constexpr int RPV = PPV / 2;  // descriptor words per 16-byte vector: 1 (fp32: 2 pairs) or 4 (int8: 8 pairs)
+    int my_nvec = 0;              // vectors of a whole chunk this lane stores
     if (kHasObs) {
         if (cached) {
-            // fp32: one register = the two pairs of one 16-byte vector; int8: four registers = 8 pairs
-            constexpr int RPV = PPV / 2;
+            my_nvec = max(0, (chunk_pairs / PPV - T.lane + 31) / 32);
 #pragma unroll
-            for (int r = 0; r < (kCanCache ? kDescRegs : 1); ++r) {
-                const int v = T.lane + 32 * (r / RPV);
-                const int P = v * PPV + 2 * (r % RPV);
-                desc[r] = (P + 1 < chunk_pairs) ? ((unsigned)gather_index(p, P) | ((unsigned)gather_index(p, P + 1) << 16)) : 0u;
+            for (int q = 0; q < kDescRegs / 4; ++q) {
+                unsigned d[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int r = q * 4 + c;
+                    const int P = (T.lane + 32 * (r / RPV)) * PPV + 2 * (r % RPV);
+                    d[c] = (P + 1 < chunk_pairs) ? ((unsigned)gather_index(p, P) | ((unsigned)gather_index(p, P + 1) << 16)) : 0u;
+                }
+                desc_sm[q * kThreads] = make_uint4(d[0], d[1], d[2], d[3]);
             }
         } else {
             for (int P = threadIdx.x; P < p.lut_entries; P += blockDim.x) lut[P] = (uint16_t)gather_index(p, P);
         }
         if (T.lane == 0) { stage[0] = mk_pair<OT>(p.DC, p.D); stage[1] = mk_pair<OT>(p.DL, p.DR); stage[2] = mk_pair<OT>(-1, -1); }
+    }
+    // distance rewards as float32 tables: entry d+kRtabOff holds float((double)(-d) * f) / float((double)d * f),
+    // i.e. the reference's float64 product (rewards.py:85,99,127) rounded once — no FP64 in the loop
+    float *rtab_neg = reinterpret_cast<float *>(smem + p.off_rtab), *rtab_pos = rtab_neg + kRtabSize;
+    if (kMoves && p.reward_kind <= CC_REWARD_SIMPLE_DISTANCE) {
+        const double f = p.reward_kind == CC_REWARD_DEFAULT ? p.rp[3] : p.rp[0];
+        for (int i = threadIdx.x; i < kRtabSize; i += blockDim.x) {
+            const int d = i - kRtabOff;
+            rtab_neg[i] = (float)((double)(-d) * f);
+            rtab_pos[i] = (float)((double)d * f);
+        }
     }
     // static map of walkable lattice points (collectivecrossing.py:509-534), one bit per point of
     // the padded lattice; the padding ring is not walkable, so neighbour tests need no bounds check
@@ -263,8 +288,12 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
     __syncthreads();
 
     // per-thread statistics (only tile leaders contribute)
-    unsigned st_steps = 0, st_episodes = 0, st_term = 0, st_trunc = 0, st_arrivals = 0, st_eplen = 0;
-    double st_epret = 0.0, st_rsum = 0.0;
+    // statistics: arrivals and the reward sum change every step and stay in registers; the
+    // episode-end sums are updated on the (rare) step an episode ends, in the warp's smem slot
+    unsigned long long *red = reinterpret_cast<unsigned long long *>(smem + p.off_red) + warp * kStCount;
+    if (kMoves && T.lane < kStCount) red[T.lane] = 0ull;
+    unsigned st_arrivals = 0;
+    double st_rsum = 0.0;
     int errbits = 0;
 
     int aidx[APL];
@@ -433,17 +462,23 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
                     if (env_ok && avalid[k] && (unsigned)action[k] > 4u) errbits |= kErrInvalidAction;
                     req[k] = make_request(pos[k], cell[k], action[k], cmp[k]);
                 }
+                auto turn = [&](const int s, const int l) {
+                    const unsigned rq = T.tshfl(req[s], l);
+                    bool hit = false;
 #pragma unroll
-                for (int s = 0; s < APL; ++s) {
-                    const int lim = min(LPE, A - s * LPE);
-#pragma unroll 8
-                    for (int l = 0; l < lim; ++l) {
-                        const unsigned rq = T.tshfl(req[s], l);
-                        bool hit = false;
+                    for (int k = 0; k < APL; ++k) hit |= cmp[k] == rq;
+                    const unsigned occ = __ballot_sync(kFull, hit) & tile_bits;
+                    if (T.li == l && rq != kNoMove && !occ) { pos[s] = rq; cmp[s] = rq; }   // :406-408
+                };
+                if (APL == 1 && A == LPE) {
 #pragma unroll
-                        for (int k = 0; k < APL; ++k) hit |= cmp[k] == rq;
-                        const unsigned occ = __ballot_sync(kFull, hit) & tile_bits;
-                        if (T.li == l && rq != kNoMove && !occ) { pos[s] = rq; cmp[s] = rq; }   // :406-408
+                    for (int l = 0; l < LPE; ++l) turn(0, l);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < APL; ++s) {
+                        const int lim = min(LPE, A - s * LPE);
+#pragma unroll 4
+                        for (int l = 0; l < lim; ++l) turn(s, l);
                     }
                 }
             } else {
@@ -478,58 +513,58 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
 
             // ---- :210-212 deactivate arrivals; rewards; terminated; truncated --------------
             bool arr[APL];
-            int n_arrived_now = 0;
-            bool lane_not_arr = false;
+            bool lane_not_arr = false, lane_new_arr = false;
 #pragma unroll
             for (int k = 0; k < APL; ++k) {
                 const int dest = aidx[k] < p.B ? p.YB : p.YE;          // :663-683 (y only)
                 arr[k] = avalid[k] && pos_y(pos[k]) == dest;
-                const bool newly = arr[k] && (fl[k] & CC_F_ACTIVE);
-                if (newly) fl[k] &= ~(unsigned)CC_F_ACTIVE;            // types.py:46-51
-                n_arrived_now += __popc(__ballot_sync(kFull, env_ok && newly) & tile_bits);
+                const bool newly = env_ok && arr[k] && (fl[k] & CC_F_ACTIVE);
+                if (arr[k]) fl[k] &= ~(unsigned)CC_F_ACTIVE;           // types.py:46-51
+                if (APL == 1) lane_new_arr = newly;
+                else st_arrivals += __popc(__ballot_sync(kFull, newly));   // counted warp-wide on every lane; lane 0's copy is used
                 lane_not_arr = lane_not_arr || (avalid[k] && !arr[k]);
             }
+            if (APL == 1) st_arrivals += __popc(__ballot_sync(kFull, lane_new_arr));
             const bool all_arrived = (__ballot_sync(kFull, lane_not_arr) & tile_bits) == 0u;
             const bool over_limit = step >= p.max_steps;                // truncateds.py:61
             bool lane_alive = false;
             float rsum_lane = 0.f;
-            double rew[APL];
+            float rew[APL];
             unsigned oflag[APL];
 #pragma unroll
             for (int k = 0; k < APL; ++k) {
                 const int x = pos_x(pos[k]), y = pos_y(pos[k]);
                 const bool boarding = aidx[k] < p.B;
-                double r = 0.0;
+                float r = 0.f;
                 if (alive_prev[k]) {                                    // rewards.py:65-66 etc.
                     switch (p.reward_kind) {
                     case CC_REWARD_DEFAULT:                             // rewards.py:68-99
-                        if (boarding) {
-                            if (arr[k]) r = p.rp[0];
-                            else if (at_tram_door(p, x, y)) r = p.rp[1];
-                            else if (in_tram_area(p, x, y)) r = p.rp[2];
-                            else r = (double)(-(abs(x - p.DC) + (p.D - y))) * p.rp[3];
+                        if (arr[k]) r = p.rpf[0];                       // :78-79 and :88-89 (same parameter, sic)
+                        else if (boarding) {
+                            if (at_tram_door(p, x, y)) r = p.rpf[1];
+                            else if (in_tram_area(p, x, y)) r = p.rpf[2];
+                            else r = rtab_neg[abs(x - p.DC) + (p.D - y) + kRtabOff];    // :82-85
                         } else {
-                            if (arr[k]) r = p.rp[0];
-                            else if (!in_tram_area(p, x, y)) r = p.rp[2];
-                            else r = (double)(abs(x - p.DC) + (y - p.D)) * p.rp[3];
+                            if (!in_tram_area(p, x, y)) r = p.rpf[2];
+                            else r = rtab_pos[abs(x - p.DC) + (y - p.D) + kRtabOff];    // :95-99 (positive, sic)
                         }
                         break;
                     case CC_REWARD_SIMPLE_DISTANCE:                     // rewards.py:120-129
-                        r = (double)(-abs(y - (boarding ? p.YB : p.YE))) * p.rp[0];
+                        r = rtab_neg[abs(y - (boarding ? p.YB : p.YE)) + kRtabOff];
                         break;
-                    case CC_REWARD_BINARY: r = p.rp[1]; break;          // rewards.py:152-159 (never goal_reward)
-                    default: r = p.rp[0]; break;                        // rewards.py:179-182
+                    case CC_REWARD_BINARY: r = p.rpf[1]; break;         // rewards.py:152-159 (never goal_reward)
+                    default: r = p.rpf[0]; break;                       // rewards.py:179-182
                     }
                 }
                 rew[k] = r;
-                rsum_lane += (float)r;
+                rsum_lane += r;
                 lane_alive |= alive_prev[k];
                 const bool tval = (p.terminated_kind == CC_TERM_ALL_AT_DESTINATION) ? all_arrived : arr[k];  // terminateds.py:56-60,82
                 const bool cval = alive_prev[k] && over_limit;          // truncateds.py:57-61
-                bool newly_done = false;                                // collectivecrossing.py:229-241
-                if (tval && !(fl[k] & CC_F_TERMINATED)) { fl[k] |= CC_F_TERMINATED; newly_done = true; }
-                if (cval && !(fl[k] & CC_F_TRUNCATED)) { fl[k] |= CC_F_TRUNCATED; newly_done = true; }
-                const bool present = !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED)) || newly_done;  // :243
+                // collectivecrossing.py:229-243: sticky flags; an entry is returned for agents that were
+                // alive at step start and for agents whose terminated flag flips now
+                const bool present = alive_prev[k] || (tval && !(fl[k] & CC_F_TERMINATED));
+                fl[k] |= (tval ? (unsigned)CC_F_TERMINATED : 0u) | (cval ? (unsigned)CC_F_TRUNCATED : 0u);
                 oflag[k] = (fl[k] & 7u) | (alive_prev[k] ? CC_O_ALIVE_PREV : 0u) | (tval ? CC_O_TERM_VALUE : 0u) |
                            (cval ? CC_O_TRUNC_VALUE : 0u) | (present ? CC_O_OBS_PRESENT : 0u);
             }
@@ -549,8 +584,25 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
 #pragma unroll
             for (int k = 0; k < APL; ++k)
                 if (env_ok && avalid[k]) {
-                    if (p.reward_f64) (reinterpret_cast<double *>(p.reward) + row0)[off[k]] = rew[k];
-                    else (reinterpret_cast<float *>(p.reward) + row0)[off[k]] = (float)rew[k];
+                    if (p.reward_f64) {
+                        // single-env facade: the reference's float64 value itself
+                        const int x = pos_x(pos[k]), y = pos_y(pos[k]);
+                        const bool boarding = aidx[k] < p.B;
+                        double r = 0.0;
+                        if (alive_prev[k]) {
+                            switch (p.reward_kind) {
+                            case CC_REWARD_DEFAULT:
+                                if (arr[k]) r = p.rp[0];
+                                else if (boarding) r = at_tram_door(p, x, y) ? p.rp[1] : in_tram_area(p, x, y) ? p.rp[2] : (double)(-(abs(x - p.DC) + (p.D - y))) * p.rp[3];
+                                else r = !in_tram_area(p, x, y) ? p.rp[2] : (double)(abs(x - p.DC) + (y - p.D)) * p.rp[3];
+                                break;
+                            case CC_REWARD_SIMPLE_DISTANCE: r = (double)(-abs(y - (boarding ? p.YB : p.YE))) * p.rp[0]; break;
+                            case CC_REWARD_BINARY: r = p.rp[1]; break;
+                            default: r = p.rp[0]; break;
+                            }
+                        }
+                        (reinterpret_cast<double *>(p.reward) + row0)[off[k]] = r;
+                    } else (reinterpret_cast<float *>(p.reward) + row0)[off[k]] = rew[k];
                     (p.agent_flags + row0)[off[k]] = (uint8_t)oflag[k];
                     if (p.agent_info) {                                 // :248-254
                         const int x = pos_x(pos[k]), y = pos_y(pos[k]);
@@ -558,13 +610,19 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
                                                                   ((fl[k] & CC_F_ACTIVE) ? CC_I_ACTIVE : 0) | (arr[k] ? CC_I_AT_DESTINATION : 0));
                     }
                 }
-            if (env_ok && T.li == 0) {
-                st_steps += 1;
-                st_arrivals += n_arrived_now;
-                st_rsum += (double)rsum;
-                if (done && any_alive) {
-                    st_episodes += 1; st_term += term_all; st_trunc += trunc_all;
-                    st_eplen += step; st_epret += (double)ep_ret;
+            const bool leader = env_ok && T.li == 0;
+            if (leader) st_rsum += (double)rsum;
+            const bool ended = leader && done && any_alive;             // the step the last agents finished on
+            const unsigned ended_mask = __ballot_sync(kFull, ended);
+            if (ended_mask) {                                           // rare: fold this warp's finished episodes into its slot
+                unsigned n_term = __popc(__ballot_sync(kFull, ended && term_all)), n_trunc = __popc(__ballot_sync(kFull, ended && trunc_all));
+                unsigned len = ended ? (unsigned)step : 0u;
+                double ret = ended ? (double)ep_ret : 0.0;
+#pragma unroll
+                for (int w = 16; w >= 1; w >>= 1) { len += __shfl_xor_sync(kFull, len, w); ret += __shfl_xor_sync(kFull, ret, w); }
+                if (T.lane == 0) {
+                    red[kStEpisodes] += __popc(ended_mask); red[kStTermAll] += n_term; red[kStTruncAll] += n_trunc; red[kStEpLen] += len;
+                    red[kStEpRet] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)red[kStEpRet]) + ret);
                 }
             }
             need_reset = env_ok && done && p.auto_reset;
@@ -688,29 +746,35 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
                 if (kCanCache && cached) {
                     // descriptors exist per whole chunk: store only the pairs of reset envs
                     P2 *out = reinterpret_cast<P2 *>(obs) + gp0;
-                    constexpr int RPV = PPV / 2;
 #pragma unroll
-                    for (int r = 0; r < kDescRegs; ++r) {
-                        const int P = (T.lane + 32 * (r / RPV)) * PPV + 2 * (r % RPV);
-                        if (P + 1 < envs_here * p.pairs_per_env) {
-                            const int e0 = P / p.pairs_per_env, e1 = (P + 1) / p.pairs_per_env;
-                            if ((tiles >> (e0 * LPE)) & 1u) out[P] = stage[desc[r] & 0xffffu];
-                            if ((tiles >> (e1 * LPE)) & 1u) out[P + 1] = stage[desc[r] >> 16];
+                    for (int q = 0; q < kDescRegs / 4; ++q) {
+                        const uint4 d4 = desc_sm[q * kThreads];
+                        const unsigned d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int r = q * 4 + c;
+                            const int P = (T.lane + 32 * (r / RPV)) * PPV + 2 * (r % RPV);
+                            if (P + 1 < envs_here * p.pairs_per_env) {
+                                const int e0 = P / p.pairs_per_env, e1 = (P + 1) / p.pairs_per_env;
+                                if ((tiles >> (e0 * LPE)) & 1u) out[P] = stage[d[c] & 0xffffu];
+                                if ((tiles >> (e1 * LPE)) & 1u) out[P + 1] = stage[d[c] >> 16];
+                            }
                         }
                     }
                 }
             } else if (kCanCache && cached && envs_here == EPW) {
-                // whole, vector-aligned chunk: gather through the register-resident descriptors
+                // whole, vector-aligned chunk: gather through the per-lane descriptors
                 uint4 *outv = reinterpret_cast<uint4 *>(reinterpret_cast<P2 *>(obs) + gp0) + T.lane;
-                const int nvec = chunk_pairs / PPV;
-                constexpr int RPV = PPV / 2;
+                uint4 d4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int j = 0; j < kDescRegs / RPV; ++j) {
-                    if (T.lane + 32 * j < nvec) {
+                    if ((j * RPV) % 4 == 0) d4 = desc_sm[(j * RPV / 4) * kThreads];
+                    if (j < my_nvec) {
+                        const unsigned dd[4] = {d4.x, d4.y, d4.z, d4.w};
                         union { uint4 u; P2 e[PPV]; } pk;
 #pragma unroll
                         for (int h = 0; h < RPV; ++h) {
-                            const unsigned d = desc[j * RPV + h];
+                            const unsigned d = dd[(j * RPV + h) % 4];
                             pk.e[2 * h] = stage[d & 0xffffu];
                             pk.e[2 * h + 1] = stage[d >> 16];
                         }
@@ -731,40 +795,28 @@ __global__ void __launch_bounds__(kThreads) cc_kernel(const __grid_constant__ KP
         }
     }
 
-    // ---- statistics: warp shuffle -> shared memory -> one atomic per slot per CTA -----------------
+    // ---- statistics: per-warp slots in shared memory -> one atomic per slot per CTA ----------------
     if (MODE == kModeStep) {
-        unsigned long long *red = reinterpret_cast<unsigned long long *>(smem + p.off_red);
-        unsigned iv[6] = {st_steps, st_episodes, st_term, st_trunc, st_arrivals, st_eplen};
-        double dv[2] = {st_epret, st_rsum};
-        unsigned long long iv64[6];
+        // every lane counted arrivals warp-wide: lane 0's copy is the warp's count
+        double rs = st_rsum;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            // counts per lane fit 32 bits; widen before the cross-lane sum
-            unsigned long long v = iv[i];
-#pragma unroll
-            for (int w = 16; w >= 1; w >>= 1) v += __shfl_xor_sync(kFull, v, w);
-            iv64[i] = v;
-        }
-#pragma unroll
-        for (int w = 16; w >= 1; w >>= 1) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) dv[i] += __shfl_xor_sync(kFull, dv[i], w);
-        }
+        for (int w = 16; w >= 1; w >>= 1) rs += __shfl_xor_sync(kFull, rs, w);
         if (T.lane == 0) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) red[warp * kStCount + i] = iv64[i];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) red[warp * kStCount + 6 + i] = (unsigned long long)__double_as_longlong(dv[i]);
+            red[kStArrivals] += st_arrivals;
+            red[kStRewardSum] = (unsigned long long)__double_as_longlong(rs);
         }
         __syncthreads();
-        if (threadIdx.x < 6) {
-            unsigned long long s = 0;
-            for (int w = 0; w < kWarpsPerCta; ++w) s += red[w * kStCount + threadIdx.x];
-            if (s) atomicAdd(&p.stats[threadIdx.x], s);
-        } else if (threadIdx.x < 8) {
-            double s = 0.0;
-            for (int w = 0; w < kWarpsPerCta; ++w) s += __longlong_as_double((long long)red[w * kStCount + threadIdx.x]);
-            if (s != 0.0) atomicAdd(reinterpret_cast<double *>(&p.stats[threadIdx.x]), s);
+        const unsigned long long *all = reinterpret_cast<unsigned long long *>(smem + p.off_red);
+        if (threadIdx.x >= 1 && threadIdx.x < 6) {
+            unsigned long long v = 0;
+            for (int w = 0; w < kWarpsPerCta; ++w) v += all[w * kStCount + threadIdx.x];
+            if (v) atomicAdd(&p.stats[threadIdx.x], v);
+        } else if (threadIdx.x == 6 || threadIdx.x == 7) {
+            double v = 0.0;
+            for (int w = 0; w < kWarpsPerCta; ++w) v += __longlong_as_double((long long)all[w * kStCount + threadIdx.x]);
+            if (v != 0.0) atomicAdd(reinterpret_cast<double *>(&p.stats[threadIdx.x]), v);
+        } else if (threadIdx.x == 0 && blockIdx.x == 0) {
+            atomicAdd(&p.stats[kStEnvSteps], (unsigned long long)p.n_envs);
         }
     }
     if (errbits) atomicOr(p.err, errbits);
