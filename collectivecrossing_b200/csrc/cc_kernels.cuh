@@ -217,7 +217,7 @@ constexpr int kRtabOff = 256, kRtabSize = 768;  // distance range of int8 coordi
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
 template <int LPE, int APL, int OBS, int MODE>
-__global__ void __launch_bounds__(kThreads, CCB_MIN_BLOCKS) cc_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CCB_MIN_BLOCKS : 1) cc_kernel(const __grid_constant__ KParams p) {
     using TL_ = Tile<LPE, APL>;
     using OT = typename std::conditional<OBS == CC_OBS_FP32, float, int8_t>::type;
     using P2 = typename PairOf<OT>::type;
