@@ -181,11 +181,14 @@ class BatchedCollectiveCrossing:
         _native.check(self._lib.cc_reset(self._h, mptr, optr, self.obs_code, self._stream()))
         return self.obs
 
-    def reset_seeded(self, seeds: torch.Tensor) -> torch.Tensor | None:
-        """``reset(seed=seeds[n])`` per env, bit-exact with the reference's PCG64 placement."""
-        seeds = self._check_tensor(seeds, torch.int64, (self.num_envs,), "seeds")
+    def reset_seeded(self, seeds: torch.Tensor | None) -> torch.Tensor | None:
+        """``reset(seed=seeds[n])`` per env, bit-exact with the reference's PCG64 placement;
+        ``seeds=None`` is ``reset()``: every env continues the generator it was last seeded with."""
+        sptr = None
+        if seeds is not None:
+            sptr = self._check_tensor(seeds, torch.int64, (self.num_envs,), "seeds").data_ptr()
         optr = self.obs.data_ptr() if self.obs is not None else None
-        _native.check(self._lib.cc_reset_seeded(self._h, seeds.data_ptr(), optr, self.obs_code, self._stream()))
+        _native.check(self._lib.cc_reset_seeded(self._h, sptr, optr, self.obs_code, self._stream()))
         return self.obs
 
     # ---- the hot path --------------------------------------------------------------------------

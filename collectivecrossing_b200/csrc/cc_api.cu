@@ -51,6 +51,8 @@ struct cc_handle {
     void *own_block = nullptr;
     unsigned long long *stats = nullptr;
     int *err = nullptr;
+    ccb::Pcg64State *gen = nullptr;  // per-env numpy-compatible generators (allocated on first seeded reset)
+    bool gen_seeded = false;
     int64_t launches = 0;
     // host-path staging
     void *stage_block = nullptr;
@@ -232,6 +234,7 @@ void cc_destroy(cc_handle *h) {
     cudaDeviceSynchronize();
     if (h->own_block) cudaFree(h->own_block);
     if (h->stage_block) cudaFree(h->stage_block);
+    if (h->gen) cudaFree(h->gen);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -371,16 +374,22 @@ int cc_policy_actions(cc_handle *h, int32_t policy, int8_t *actions_out, void *s
 }
 
 int cc_reset_seeded(cc_handle *h, const int64_t *seeds, void *obs, int32_t obs_dtype, void *stream) {
-    if (!h || !seeds) return fail(CC_ERR_INVALID_ARG, "null handle or seeds");
+    if (!h) return fail(CC_ERR_INVALID_ARG, "null handle");
+    if (!seeds && !h->gen_seeded) return fail(CC_ERR_INVALID_ARG, "cc_reset_seeded(seeds = NULL) continues the stored generators: seed them first");
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!h->gen) {
+        cudaError_t e = cudaMalloc(&h->gen, (size_t)h->n_envs * sizeof(ccb::Pcg64State));
+        if (e != cudaSuccess) return fail(CC_ERR_NOMEM, "cudaMalloc for generator states: %s", cudaGetErrorString(e));
+    }
     KParams p;
     fill_params(h, p, CC_OBS_NONE, false);
     const int threads = 128;
     const long long blocks = (h->n_envs + threads - 1) / threads;
-    ccb::cc_reset_seeded_kernel<<<(unsigned)blocks, threads, 0, s>>>(p, reinterpret_cast<const long long *>(seeds));
+    ccb::cc_reset_seeded_kernel<<<(unsigned)blocks, threads, 0, s>>>(p, reinterpret_cast<const long long *>(seeds), h->gen);
     CC_CUDA(cudaGetLastError());
     h->launches += 1;
+    h->gen_seeded = true;
     if (obs && obs_dtype != CC_OBS_NONE) return cc_observe(h, obs, obs_dtype, stream);
     return CC_OK;
 }

@@ -890,11 +890,21 @@ struct Pcg64 {
     }
 };
 
-__global__ void __launch_bounds__(128) cc_reset_seeded_kernel(const __grid_constant__ KParams p, const long long *seeds) {
+// persistent generator of one env (what gymnasium keeps in env.np_random): 6 x 8 bytes
+struct Pcg64State { unsigned long long hi, lo, inc_hi, inc_lo, buffered, has_buffered; };
+
+// seeds != nullptr: reset(seed=seeds[n]) — a fresh generator per env (gymnasium Env.reset(seed=s));
+// seeds == nullptr: reset() — every env keeps drawing from its stored generator.
+__global__ void __launch_bounds__(128) cc_reset_seeded_kernel(const __grid_constant__ KParams p, const long long *seeds, Pcg64State *gen) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.n_envs) return;
     Pcg64 g;
-    g.seed((unsigned long long)seeds[n]);
+    if (seeds) g.seed((unsigned long long)seeds[n]);
+    else {
+        const Pcg64State st = gen[n];
+        g.hi = st.hi; g.lo = st.lo; g.inc_hi = st.inc_hi; g.inc_lo = st.inc_lo;
+        g.buffered = (unsigned)st.buffered; g.has_buffered = st.has_buffered != 0;
+    }
     int8_t *x = p.x + n * p.A, *y = p.y + n * p.A;
     int stuck = 0;
     for (int i = 0; i < p.A; ++i) {
@@ -916,6 +926,7 @@ __global__ void __launch_bounds__(128) cc_reset_seeded_kernel(const __grid_const
     }
     p.step[n] = 0;
     p.ep_ret[n] = 0.f;
+    gen[n] = Pcg64State{g.hi, g.lo, g.inc_hi, g.inc_lo, (unsigned long long)g.buffered, g.has_buffered ? 1ull : 0ull};
     if (stuck) atomicOr(p.err, kErrResetStuck);
 }
 

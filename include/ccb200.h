@@ -202,7 +202,9 @@ int cc_reset(cc_handle *h, const uint8_t *mask, void *obs, int32_t obs_dtype, vo
 
 /* Replaces reset(seed=s) bit-exactly: per-env numpy Generator(PCG64(SeedSequence(seed)))
  * (gymnasium's seeding, used at collectivecrossing.py:95,105-106,134-137).
- * seeds: [N] int64 (device). */
+ * seeds: [N] int64 (device) seeds every env's generator afresh, like reset(seed=s).
+ * seeds == NULL is reset() without a seed: every env keeps drawing from the generator it was
+ * last seeded with (gymnasium keeps env.np_random across resets); an error before any seeding. */
 int cc_reset_seeded(cc_handle *h, const int64_t *seeds, void *obs, int32_t obs_dtype,
                     void *stream);
 

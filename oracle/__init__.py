@@ -46,7 +46,7 @@ _EXPORTS = {
     "cc_oracle_reset": (C.c_int, [C.POINTER(_abi.CCConfig), _I64, _I64, _U64, _U64, _P, _P, _P, _P, _P, _P, _P, _I32]),
     "cc_oracle_policy_actions": (C.c_int, [C.POINTER(_abi.CCConfig), _I64, _I64, _U64, _U64, _I32, _P, _P, _P, _P, _P]),
     "cc_oracle_observe": (C.c_int, [C.POINTER(_abi.CCConfig), _I64, _P, _P, _P, _P, _P, _I32]),
-    "cc_oracle_reset_seeded": (C.c_int, [C.POINTER(_abi.CCConfig), _I64, _P, _P, _P, _P, _P, _P, _P, _I32]),
+    "cc_oracle_reset_seeded": (C.c_int, [C.POINTER(_abi.CCConfig), _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I32]),
     "cc_oracle_pcg64_integers": (None, [_U64, _I64, _I64, _I64, _P]),
     "cc_oracle_philox4x32_10": (None, [_P, _P, _P]),
     "cc_oracle_abi_version": (C.c_int, []),
@@ -156,9 +156,13 @@ class OracleEnvs:
         return b["obs"]
 
     def reset_seeded(self, seeds, obs_dtype=_abi.OBS_INT8):
+        """seeds: int64 per env (reset(seed=s)); None continues the stored generators (reset())."""
         b = self._bufs(obs_dtype, _abi.REWARD_F32)
-        seeds = np.ascontiguousarray(seeds, np.int64).reshape(self.n)
-        rc = lib().cc_oracle_reset_seeded(C.byref(self.cfg), self.n, _ptr(seeds), _ptr(self.x), _ptr(self.y),
+        if not hasattr(self, "gen"):
+            self.gen = np.zeros((self.n, 6), np.uint64)
+        if seeds is not None:
+            seeds = np.ascontiguousarray(seeds, np.int64).reshape(self.n)
+        rc = lib().cc_oracle_reset_seeded(C.byref(self.cfg), self.n, _ptr(seeds), _ptr(self.gen), _ptr(self.x), _ptr(self.y),
                                           _ptr(self.flags), _ptr(self.step_count), _ptr(self.episode_return),
                                           _ptr(b["obs"]), obs_dtype)
         if rc != _abi.OK:
