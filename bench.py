@@ -149,38 +149,48 @@ def _py_worker(job):
     return steps, time.perf_counter() - t0
 
 
-def cpu_python_port(args, seconds):
+def cpu_python_port(args, seconds, pool=None):
     """The reference's own shape of computation: a pure-Python env + policy loop, one independent
     env per host core (multiprocessing), reset() on episode end."""
     import multiprocessing as mp
 
     cores = os.cpu_count() or 1
-    with mp.get_context("spawn").Pool(cores) as pool:
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores)
+    try:
         res = pool.map(_py_worker, [(args.policy, seconds, 1000 + k) for k in range(cores)])
+    finally:
+        if own:
+            pool.close()
     rate = sum(s / dt for s, dt in res) * 8
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"pure-Python port of the reference loop (oracle/pyport.py), {cores} processes x 1 env, "
-                      f"{sum(s for s, _ in res)} env-steps in {seconds:.0f} s each, {args.policy} policy + step + reset on done"}
+                      f"{sum(s for s, _ in res)} env-steps in {seconds:.1f} s each, {args.policy} policy + step + reset on done"}
 
 
 def run_reference(args):
+    """`--impl reference`: the reference is a pure-Python package that cannot travel to the GPU box
+    (tier rule), so its arm is the oracle's Python port of the same loop on all host cores.  A step
+    is a bounded sample: every core runs the loop for a fixed time slice."""
+    import multiprocessing as mp
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step_seconds = max(1.0, min(6.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    info = None
-    for k in range(args.warmup + args.steps):
-        info = cpu_python_port(args, per_step_seconds)
-        if k >= args.warmup:
-            vals.append(info["value"])
-        if k >= args.warmup and len(vals) >= 3 and (k + 1) * per_step_seconds > 150:
-            break
+    total = args.warmup + args.steps
+    slice_s = max(0.25, min(4.0, 100.0 / max(1, total)))
+    vals, info = [], None
+    with mp.get_context("spawn").Pool(os.cpu_count() or 1) as pool:
+        for k in range(total):
+            info = cpu_python_port(args, slice_s, pool)
+            if k >= args.warmup:
+                vals.append(info["value"])
     value = sum(vals) / len(vals)
     info["value"] = value
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": per_step_seconds * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": slice_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "python int / float64", "data": "synthetic", "config": config_dict(args, args.envs * args.gpus),
         "cpu_baseline": info, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -214,7 +224,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from collectivecrossing_b200 import BatchedCollectiveCrossing
+    from collectivecrossing_b200.distributed import ShardedCollectiveCrossing
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -228,7 +238,10 @@ def run_ours(args):
     cfg = workload_config()
     n = args.envs
     A = 8
-    env = BatchedCollectiveCrossing(cfg, n, dev, seed=2026, global_env_offset=rank * n, obs_dtype=args.obs_dtype, auto_reset=True)
+    # contiguous shard per rank; the RNG is keyed on the global env index (collectivecrossing_b200/distributed.py)
+    sharded = ShardedCollectiveCrossing(cfg, n * world, seed=2026, device=dev, obs_dtype=args.obs_dtype, auto_reset=True)
+    env = sharded.env
+    assert sharded.count == n and sharded.offset == rank * n
     env.reset()
     for _ in range(args.warmup):
         env.step(policy=args.policy)
@@ -243,12 +256,7 @@ def run_ours(args):
     env.check_error()
 
     # episode statistics: the one collective of the job (NCCL all-reduce of 8 scalars per chunk)
-    st = env.stats()
-    if world > 1:
-        keys = list(st)
-        t = torch.tensor([float(st[k]) for k in keys], device=dev, dtype=torch.float64)
-        dist.all_reduce(t)
-        st = dict(zip(keys, t.tolist()))
+    st = sharded.global_stats()
 
     agent_steps = float(n) * A * args.steps * world
     value = agent_steps / (ms * 1e-3)
