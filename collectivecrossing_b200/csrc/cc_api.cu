@@ -85,6 +85,8 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     int off = round_up(p.lut_entries * 2, 16);
     p.off_walk = off;
     off += round_up(p.walk_words * 4, 16);
+    p.off_geo = off;   // xt[W+3], yt[2][H+3] (uint32), act_tab[kPolicyRows*16] (bytes)
+    off += round_up(((c.width + 3) + 2 * (c.height + 3)) * 4 + ccb::kPolicyRows * 16, 16);
     p.off_stage = off;
     off += round_up(ccb::kWarpsPerCta * p.stage_pairs * pair_bytes, 16);
     p.off_bitmap = off;
@@ -92,7 +94,7 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     p.off_red = off;
     off += ccb::kWarpsPerCta * ccb::kStCount * 8;
     p.off_desc = off;
-    off += (obs_dtype != CC_OBS_NONE && h->lpe <= 16) ? ccb::kDescRegs * 4 * ccb::kThreads : 0;
+    off += (obs_dtype != CC_OBS_NONE && h->lpe <= 16) ? ccb::kDescWords * 4 * ccb::kThreads : 0;
     p.off_rtab = off;
     off += 2 * ccb::kRtabSize * 4;
     p.smem_total = off;
@@ -190,6 +192,7 @@ int cc_create(const cc_config *cfg, int64_t n_envs, int device, int64_t global_e
     if (cfg->num_boarding < 0 || cfg->num_exiting < 0 || A < 1 || A > CC_MAX_AGENTS)
         return fail(CC_ERR_UNSUPPORTED, "agents per env must be in 1..%d, got %d", CC_MAX_AGENTS, A);
     if (n_envs < 1) return fail(CC_ERR_INVALID_ARG, "n_envs must be positive");
+    if (n_envs * (int64_t)A >= (int64_t)1 << 31) return fail(CC_ERR_UNSUPPORTED, "n_envs * agents must stay below 2^31 per handle (32-bit slot indices)");
     const int32_t geo[] = {cfg->width, cfg->height, cfg->division_y, cfg->tram_left, cfg->tram_right, cfg->door_left, cfg->door_right, cfg->boarding_dest_y, cfg->exiting_dest_y};
     for (int32_t v : geo)
         if (v < -1 || v > 126) return fail(CC_ERR_UNSUPPORTED, "geometry value %d does not fit the int8 lattice", v);

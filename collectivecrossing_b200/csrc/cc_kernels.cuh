@@ -60,7 +60,7 @@ struct KParams {
     int lut_entries;     // EPW * A * R
     int stage_pairs;     // 3 + EPW * 2A (per warp)
     int walk_words;      // words of one padded-lattice bitmap: ceil((W+3)(H+3)/32)
-    int off_walk, off_stage, off_bitmap, off_red, off_desc, off_rtab;
+    int off_walk, off_geo, off_stage, off_bitmap, off_red, off_desc, off_rtab;
     float rpf[4];        // reward parameters rounded to float32 once
     long long n_groups;
     int smem_total;
@@ -209,9 +209,55 @@ __device__ __forceinline__ void emit_obs_lut(T *obs, long long gp0, int count, c
     }
 }
 
-constexpr int kDescRegs = 12;        // registers of cached gather descriptors per lane
-constexpr int kDescPairs = 32 * kDescRegs * 2;  // = 768 pairs per warp chunk
-constexpr int kRtabOff = 256, kRtabSize = 768;  // distance range of int8 coordinates: [-256, 511]
+constexpr int kDescWords = 24;                 // cached gather descriptors per lane (one per output pair)
+constexpr int kDescPairs = 32 * kDescWords;    // = 768 output pairs per warp chunk
+constexpr int kRtabSize = 400;                 // reward-table index = |x-DC| (<= 128) + biased y distance (< 256)
+constexpr int kYBias = 128;
+constexpr int kNumYClass = 5;                  // far / door level / beyond: up, down, at destination
+constexpr int kPolicyRows = 2 * kNumYClass * 3;  // (type, y class, x class)
+
+// Geometry tables (per CTA, built once).  A word has its additive fields in the low bits and its
+// predicate flags in the top byte, so for an agent at (x, y) of type t
+//      u = yt[t][y] + xt[x]   ->  bits 0-7  row of act_tab (greedy decision),  bits 8-16 reward-table index
+//      f = (yt & xt) >> 24    ->  bit0 in_tram_area, bit1 at_tram_door, bit3 at destination  (= CC_I_* bits)
+__device__ __forceinline__ unsigned make_xt(const KParams &p, int x) {
+    const unsigned tramx = p.TL <= x && x <= p.TR, adj = (x == p.DL - 1 || x == p.DR + 1);
+    const unsigned xcmp = x < p.DC ? 0u : (x == p.DC ? 1u : 2u);
+    const unsigned xdist = p.reward_kind == CC_REWARD_DEFAULT ? (unsigned)abs(x - p.DC) : 0u;  // rewards.py:82-84,95-98
+    return xcmp | (xdist << 8) | ((tramx | (adj << 1) | 8u) << 24);
+}
+__device__ __forceinline__ unsigned make_yt(const KParams &p, int type, int y) {
+    const int dest = type == 0 ? p.YB : p.YE;
+    const unsigned ytram = y >= p.D, isd = y == p.D, arrived = y == dest;
+    // y class of the greedy policy (greedy_policy.py:117-158)
+    unsigned cls;
+    if (type == 0) cls = y < p.D - 1 ? 0u : (y == p.D - 1 ? 1u : (y < dest ? 2u : (y > dest ? 3u : 4u)));
+    else           cls = y > p.D + 1 ? 0u : (y == p.D + 1 ? 1u : (y < dest ? 2u : (y > dest ? 3u : 4u)));
+    int ydist;
+    if (p.reward_kind == CC_REWARD_DEFAULT) ydist = type == 0 ? p.D - y : y - p.D;   // rewards.py:83,97
+    else ydist = abs(y - dest);                                                        // utils/geometry.py:54-55
+    ydist = min(max(ydist + kYBias, 0), 255);
+    return ((unsigned)(type * kNumYClass + (int)cls) * 3u) | ((unsigned)ydist << 8) | ((ytram | (isd << 1) | (arrived << 3)) << 24);
+}
+// greedy decision for (type, y class, x class) and the 4-bit mask of valid moves (bit a = action a valid):
+// baseline_policies/greedy_policy.py:64-88 (preferred move if valid) and :277-449 (fallback lists)
+__device__ __forceinline__ int greedy_decision(int row, unsigned vmask) {
+    const int type = row / (kNumYClass * 3), cls = (row / 3) % kNumYClass, xc = row % 3;
+    const int vert = type == 0 ? CC_ACT_UP : CC_ACT_DOWN, toward = xc == 0 ? CC_ACT_RIGHT : CC_ACT_LEFT;
+    int want;
+    unsigned pref;  // 4 nibbles, first choice lowest
+    if (cls <= 1) {
+        want = (cls == 1 && xc != 1) ? toward : vert;
+        if (type == 0) pref = xc == 0 ? 0x3210u : (xc == 2 ? 0x3012u : 0x3201u);   // RULD | LURD | URLD
+        else           pref = xc == 0 ? 0x1230u : (xc == 2 ? 0x1032u : 0x1203u);   // RDLU | LDRU | DRLU
+    } else {
+        want = cls == 2 ? CC_ACT_UP : (cls == 3 ? CC_ACT_DOWN : CC_ACT_WAIT);       // sign(dest - y), :178-182
+        pref = type == 0 ? 0x3201u : 0x1203u;
+    }
+    if (want == CC_ACT_WAIT || ((vmask >> want) & 1u)) return want;
+    for (int c = 0; c < 4; ++c) { const int cand = (pref >> (4 * c)) & 15; if ((vmask >> cand) & 1u) return cand; }
+    return CC_ACT_WAIT;
+}
 
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
@@ -222,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
     using OT = typename std::conditional<OBS == CC_OBS_FP32, float, int8_t>::type;
     using P2 = typename PairOf<OT>::type;
     constexpr int EPW = TL_::EPW;
-    constexpr int PPV = 16 / (int)sizeof(P2);
+    constexpr int PPV = 16 / (int)sizeof(P2);  // output pairs per 16-byte vector: 2 (fp32) or 8 (int8)
     constexpr bool kHasObs = OBS != CC_OBS_NONE;
     constexpr bool kCanCache = kHasObs && LPE <= 16;
     constexpr bool kHasPolicy = MODE == kModeStep || MODE == kModePolicy;
@@ -232,30 +278,33 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
     const TL_ T;
     const int warp = threadIdx.x >> 5;
     const int A = p.A;
+    const int PW = p.W + 3, PH = p.H + 3;  // lattice padded by one ring: x in [-1, W+1] -> column x+1
     uint16_t *lut = reinterpret_cast<uint16_t *>(smem);
     unsigned *walk = reinterpret_cast<unsigned *>(smem + p.off_walk);
+    unsigned *xt = reinterpret_cast<unsigned *>(smem + p.off_geo), *yt = xt + PW;
+    uint8_t *act_tab = reinterpret_cast<uint8_t *>(yt + 2 * PH);
+    float *rtab = reinterpret_cast<float *>(smem + p.off_rtab);   // [2][kRtabSize]
     P2 *stage = reinterpret_cast<P2 *>(smem + p.off_stage) + warp * p.stage_pairs;
     unsigned *blocked = reinterpret_cast<unsigned *>(smem + p.off_bitmap) + (warp * EPW + T.tile) * p.walk_words;
-    const int PW = p.W + 3;  // padded lattice: x in [-1, W+1] -> column x+1
 
-    // whole-chunk fast path of the observation gather: each lane's descriptors are loop-invariant;
-    // they live in shared memory as [kDescRegs/4][kThreads] uint4 (conflict-free LDS.128)
+    // ---- once per CTA: gather descriptors / LUT, geometry tables -----------------------------------
     const int chunk_pairs = EPW * p.pairs_per_env;
     const bool cached = kCanCache && chunk_pairs <= kDescPairs && (chunk_pairs % PPV) == 0;
-    uint4 *desc_sm = reinterpret_cast<uint4 *>(smem + p.off_desc) + threadIdx.x;
-    constexpr int RPV = PPV / 2;  // descriptor words per 16-byte vector: 1 (fp32: 2 pairs) or 4 (int8: 8 pairs)
-    int my_nvec = 0;              // vectors of a whole chunk this lane stores
+    uint4 *desc_sm = reinterpret_cast<uint4 *>(smem + p.off_desc) + threadIdx.x;  // [kDescWords/4][kThreads], conflict-free
+    int my_nvec = 0;  // vectors of a whole chunk this lane stores
     if (kHasObs) {
         if (cached) {
+            // descriptor = shared-memory byte address of the stage pair feeding one output pair
             my_nvec = max(0, (chunk_pairs / PPV - T.lane + 31) / 32);
+            const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(stage);
 #pragma unroll
-            for (int q = 0; q < kDescRegs / 4; ++q) {
+            for (int q = 0; q < kDescWords / 4; ++q) {
                 unsigned d[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int r = q * 4 + c;
-                    const int P = (T.lane + 32 * (r / RPV)) * PPV + 2 * (r % RPV);
-                    d[c] = (P + 1 < chunk_pairs) ? ((unsigned)gather_index(p, P) | ((unsigned)gather_index(p, P + 1) << 16)) : 0u;
+                    const int w = q * 4 + c;
+                    const int P = (T.lane + 32 * (w / PPV)) * PPV + (w % PPV);
+                    d[c] = stage_addr + (unsigned)sizeof(P2) * (unsigned)(P < chunk_pairs ? gather_index(p, P) : 0);
                 }
                 desc_sm[q * kThreads] = make_uint4(d[0], d[1], d[2], d[3]);
             }
@@ -264,15 +313,19 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
         }
         if (T.lane == 0) { stage[0] = mk_pair<OT>(p.DC, p.D); stage[1] = mk_pair<OT>(p.DL, p.DR); stage[2] = mk_pair<OT>(-1, -1); }
     }
-    // distance rewards as float32 tables: entry d+kRtabOff holds float((double)(-d) * f) / float((double)d * f),
-    // i.e. the reference's float64 product (rewards.py:85,99,127) rounded once — no FP64 in the loop
-    float *rtab_neg = reinterpret_cast<float *>(smem + p.off_rtab), *rtab_pos = rtab_neg + kRtabSize;
+    for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
+    for (int i = threadIdx.x; i < 2 * PH; i += blockDim.x) yt[i] = make_yt(p, i / PH, i % PH - 1);
+    if (kHasPolicy)
+        for (int i = threadIdx.x; i < kPolicyRows * 16; i += blockDim.x) act_tab[i] = (uint8_t)greedy_decision(i >> 4, (unsigned)i & 15u);
+    // distance rewards: entry k holds float((double)(-d) * f) (boarding / simple distance) or
+    // float((double)d * f) (exiting, default reward) for d = k - kYBias: the reference's float64 product
+    // (rewards.py:85,99,127) rounded once — no FP64 in the loop
     if (kMoves && p.reward_kind <= CC_REWARD_SIMPLE_DISTANCE) {
         const double f = p.reward_kind == CC_REWARD_DEFAULT ? p.rp[3] : p.rp[0];
-        for (int i = threadIdx.x; i < kRtabSize; i += blockDim.x) {
-            const int d = i - kRtabOff;
-            rtab_neg[i] = (float)((double)(-d) * f);
-            rtab_pos[i] = (float)((double)d * f);
+        for (int i = threadIdx.x; i < 2 * kRtabSize; i += blockDim.x) {
+            const int type = i / kRtabSize, d = i % kRtabSize - kYBias;
+            const bool negate = type == 0 || p.reward_kind == CC_REWARD_SIMPLE_DISTANCE;
+            rtab[i] = (float)((double)(negate ? -d : d) * f);
         }
     }
     // static map of walkable lattice points (collectivecrossing.py:509-534), one bit per point of
@@ -281,146 +334,116 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
         unsigned bits = 0;
         for (int b = 0; b < 32; ++b) {
             const int idx = w * 32 + b, yy = idx / PW - 1, xx = idx - (yy + 1) * PW - 1;
-            bits |= valid_position(p, xx, yy) && yy <= p.H + 1 ? (1u << b) : 0u;
+            bits |= valid_position(p, xx, yy) ? (1u << b) : 0u;
         }
         walk[w] = bits;
     }
-    __syncthreads();
-
-    // per-thread statistics (only tile leaders contribute)
     // statistics: arrivals and the reward sum change every step and stay in registers; the
     // episode-end sums are updated on the (rare) step an episode ends, in the warp's smem slot
     unsigned long long *red = reinterpret_cast<unsigned long long *>(smem + p.off_red) + warp * kStCount;
     if (kMoves && T.lane < kStCount) red[T.lane] = 0ull;
+    __syncthreads();
     unsigned st_arrivals = 0;
     double st_rsum = 0.0;
     int errbits = 0;
 
-    int aidx[APL];
+    // ---- per-lane constants ---------------------------------------------------------------------------
+    int aidx[APL], aload[APL], ytoff[APL];
     bool avalid[APL];
 #pragma unroll
-    for (int k = 0; k < APL; ++k) { aidx[k] = T.li + k * LPE; avalid[k] = aidx[k] < A; }
+    for (int k = 0; k < APL; ++k) {
+        aidx[k] = T.li + k * LPE;
+        avalid[k] = aidx[k] < A;
+        aload[k] = T.tile * A + min(aidx[k], A - 1);   // lanes beyond A re-read agent A-1 (never stored)
+        ytoff[k] = aidx[k] < p.B ? 0 : PH;              // row of yt for this agent's type
+    }
     const unsigned tile_bits = TL_::MASK << T.tshift;
+    const int group_stride = EPW * A;
 
-    const long long total_warps = (long long)gridDim.x * kWarpsPerCta;
-    for (long long g = (long long)blockIdx.x * kWarpsPerCta + warp; g < p.n_groups; g += total_warps) {
-        const long long n0 = g * EPW;
-        const long long rem = p.n_envs - n0;
-        const int envs_here = rem < EPW ? (int)rem : EPW;
-        const bool env_ok = T.tile < envs_here;
+    const int total_warps = (int)gridDim.x * kWarpsPerCta;
+    for (int g = (int)blockIdx.x * kWarpsPerCta + warp; g < (int)p.n_groups; g += total_warps) {
+        const long long n0 = (long long)g * EPW;
+        const int envs_here = (int)min((long long)EPW, p.n_envs - n0);
+        const bool env_ok = T.tile < envs_here;           // false only in the ragged last group
+        const int row0 = g * group_stride;                // first agent slot of the group (N*A < 2^31, checked by the host)
+        const int tload = env_ok ? T.tile : 0;            // tiles beyond the end re-read env 0 of the group
         const unsigned long long genv = p.genv_offset + (unsigned long long)(n0 + T.tile);
-        const long long row0 = n0 * A;             // first agent slot of the group
-        int off[APL];                               // this lane's agent slots relative to row0
+        int off[APL];
 #pragma unroll
-        for (int k = 0; k < APL; ++k) off[k] = T.tile * A + aidx[k];
+        for (int k = 0; k < APL; ++k) off[k] = row0 + (env_ok ? aload[k] : aload[k] - T.tile * A);
 
-        // ---- load the env's record (one contiguous run of bytes per array per warp) ----------
-        unsigned pos[APL];
+        // ---- load the env's record: branch-free, one contiguous run of bytes per array per warp ----
+        unsigned pos[APL];   // x << 8 | y (both 0..126 for every reachable state)
         unsigned fl[APL];
         int action[APL];
-        {
-            const int8_t *gx = p.x + row0, *gy = p.y + row0;
-            const uint8_t *gf = p.flags + row0;
 #pragma unroll
-            for (int k = 0; k < APL; ++k) {
-                pos[k] = 0; fl[k] = 0; action[k] = CC_ACT_WAIT;
-                if (env_ok && avalid[k]) {
-                    pos[k] = pack_pos(gx[off[k]], gy[off[k]]);
-                    fl[k] = gf[off[k]];
-                    if (kMoves && p.policy == CC_POLICY_EXTERNAL) action[k] = (p.actions + row0)[off[k]];
-                }
-            }
+        for (int k = 0; k < APL; ++k) {
+            pos[k] = ((unsigned)(uint8_t)p.x[off[k]] << 8) | (unsigned)(uint8_t)p.y[off[k]];
+            fl[k] = (env_ok && avalid[k]) ? (unsigned)p.flags[off[k]] : 0u;
+            action[k] = CC_ACT_WAIT;
+            if (kMoves && p.policy == CC_POLICY_EXTERNAL) action[k] = p.actions[off[k]];
         }
-        int step = env_ok ? (p.step + n0)[T.tile] : 0;
-        float ep_ret = (env_ok && kMoves) ? (p.ep_ret + n0)[T.tile] : 0.f;
+        int step = p.step[(int)n0 + tload];
+        float ep_ret = kMoves ? p.ep_ret[(int)n0 + tload] : 0.f;
 
-        // padded-lattice cell of every owned agent (centre clamped into the lattice: set_state
-        // promises in-lattice positions, the clamp only keeps shared-memory reads in bounds)
+        // table coordinates (clamped: set_state promises in-lattice positions; the clamp only keeps
+        // shared-memory reads in bounds for garbage) and the padded-lattice cell of every owned agent
         int cell[APL];
-        if (kHasPolicy) {
-#pragma unroll
-            for (int k = 0; k < APL; ++k) {
-                const int cx = min(max(pos_x(pos[k]), 0), p.W) + 1, cy = min(max(pos_y(pos[k]), 0), p.H) + 1;
-                cell[k] = cy * PW + cx;
-            }
-        }
+        unsigned geo_u[APL], geo_f[APL];
+        auto lookup = [&](int k) {
+            const int cx = min((int)(pos[k] >> 8), p.W + 1) + 1, cy = min((int)(pos[k] & 0xffu), p.H + 1) + 1;
+            const unsigned xv = xt[cx], yv = yt[ytoff[k] + cy];
+            cell[k] = cy * PW + cx;
+            geo_u[k] = yv + xv;
+            geo_f[k] = (yv & xv) >> 24;
+        };
 
         // ---- on-device policies (baseline_policies/*.py at randomness_factor 0) ---------------
         bool geo_known = false;  // chosen moves already passed the geometric test
         if (kHasPolicy && p.policy != CC_POLICY_EXTERNAL) {
             if (p.policy == CC_POLICY_RANDOM) {
 #pragma unroll
-                for (int k = 0; k < APL; ++k)
-                    if (env_ok && avalid[k]) action[k] = bounded(draw(p, genv, kStreamAction, (unsigned)aidx[k]).v0, 5);
+                for (int k = 0; k < APL; ++k) {
+                    action[k] = bounded(draw(p, genv, kStreamAction, (unsigned)aidx[k]).v0, 5);
+                    lookup(k);
+                }
             } else {
                 // blocked = walls | cells held by ACTIVE agents (collectivecrossing.py:345-369 as
                 // one bit test; the asking agent's own cell is never one of its neighbour cells)
                 for (int w = T.li; w < p.walk_words; w += LPE) blocked[w] = ~walk[w];
                 __syncwarp();
-#pragma unroll
-                for (int k = 0; k < APL; ++k)
-                    if (env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE)) atomicOr(&blocked[cell[k] >> 5], 1u << (cell[k] & 31));
-                __syncwarp();
-                // waiting_policy.py:118-131: some exiting agent that is not done has not arrived
                 bool pending = false;
 #pragma unroll
-                for (int k = 0; k < APL; ++k)
-                    pending |= env_ok && avalid[k] && aidx[k] >= p.B && !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED)) &&
-                               pos_y(pos[k]) != p.YE;
+                for (int k = 0; k < APL; ++k) {
+                    lookup(k);
+                    if (fl[k] & CC_F_ACTIVE) atomicOr(&blocked[cell[k] >> 5], 1u << (cell[k] & 31));
+                    // waiting_policy.py:118-131: some exiting agent that is not done has not arrived
+                    pending |= avalid[k] && aidx[k] >= p.B && (fl[k] & 6u) == 0u && env_ok && !(geo_f[k] & 8u);
+                }
+                __syncwarp();
                 const bool exiting_pending = p.policy == CC_POLICY_WAITING && (__ballot_sync(kFull, pending) & tile_bits) != 0u;
 #pragma unroll
                 for (int k = 0; k < APL; ++k) {
-                    int a = CC_ACT_WAIT;
-                    const bool asks = env_ok && avalid[k] && (fl[k] & 7u) == CC_F_ACTIVE;  // active, not done
-                    if (asks) {
-                        const int x = pos_x(pos[k]), y = pos_y(pos[k]);
-                        const bool boarding = aidx[k] < p.B;
-                        const bool waits = exiting_pending && boarding && !in_tram_area(p, x, y);
-                        if (!waits) {
-                            // validity of the four moves (greedy_policy.py:238-264 -> _is_move_valid)
-                            const int c = cell[k];
-                            auto is_free = [&](int idx) { return ((blocked[idx >> 5] >> (idx & 31)) & 1u) ^ 1u; };
-                            const unsigned vmask = is_free(c + 1) | (is_free(c + PW) << 1) | (is_free(c - 1) << 2) | (is_free(c - PW) << 3);
-                            // greedy_policy.py:90-161 _calculate_direction (+ :163-236); the fallback
-                            // lists (:311-449) are 4 nibbles, first choice lowest
-                            const int D = p.D, dc = p.DC;
-                            const int toward_dc = x < dc ? CC_ACT_RIGHT : CC_ACT_LEFT;
-                            int want;
-                            unsigned pref;
-                            if (boarding) {
-                                if (y < D) {
-                                    want = (y == D - 1 && x != dc) ? toward_dc : CC_ACT_UP;
-                                    pref = (x < dc) ? 0x3210u : (x > dc) ? 0x3012u : 0x3201u;  // RULD | LURD | URLD
-                                } else {
-                                    want = y < p.YB ? CC_ACT_UP : y > p.YB ? CC_ACT_DOWN : CC_ACT_WAIT;
-                                    pref = 0x3201u;
-                                }
-                            } else {
-                                if (y > D) {
-                                    want = (y == D + 1 && x != dc) ? toward_dc : CC_ACT_DOWN;
-                                    pref = (x < dc) ? 0x1230u : (x > dc) ? 0x1032u : 0x1203u;  // RDLU | LDRU | DRLU
-                                } else {
-                                    want = y > p.YE ? CC_ACT_DOWN : y < p.YE ? CC_ACT_UP : CC_ACT_WAIT;
-                                    pref = 0x1203u;
-                                }
-                            }
-                            if (want == CC_ACT_WAIT || ((vmask >> want) & 1u)) a = want;
-                            else {
-#pragma unroll
-                                for (int cnd = 3; cnd >= 0; --cnd) { const int cand = (pref >> (4 * cnd)) & 15; if ((vmask >> cand) & 1u) a = cand; }
-                            }
-                        }
-                    }
-                    action[k] = a;
+                    // validity of the four moves (greedy_policy.py:238-264 -> _is_move_valid)
+                    const int c = cell[k];
+                    auto is_free = [&](int idx) { return ((blocked[idx >> 5] >> (idx & 31)) & 1u) ^ 1u; };
+                    const unsigned vmask = is_free(c + 1) | (is_free(c + PW) << 1) | (is_free(c - 1) << 2) | (is_free(c - PW) << 3);
+                    const int a = act_tab[((geo_u[k] & 0xffu) << 4) | vmask];
+                    const bool asks = (fl[k] & 7u) == CC_F_ACTIVE;                         // active, not done
+                    const bool waits = exiting_pending && aidx[k] < p.B && !(geo_f[k] & 1u);  // waiting_policy.py:74-108
+                    action[k] = (asks && !waits) ? a : CC_ACT_WAIT;
                 }
                 geo_known = true;
                 __syncwarp();
             }
+        } else if (kHasPolicy) {
+#pragma unroll
+            for (int k = 0; k < APL; ++k) lookup(k);
         }
         if (MODE == kModePolicy) {
 #pragma unroll
             for (int k = 0; k < APL; ++k)
-                if (env_ok && avalid[k]) (p.actions_out + row0)[off[k]] = (int8_t)action[k];
+                if (env_ok && avalid[k]) p.actions_out[off[k]] = (int8_t)action[k];
             continue;
         }
 
@@ -430,13 +453,13 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             if (p.actions_out) {
 #pragma unroll
                 for (int k = 0; k < APL; ++k)
-                    if (env_ok && avalid[k]) (p.actions_out + row0)[off[k]] = (int8_t)action[k];
+                    if (env_ok && avalid[k]) p.actions_out[off[k]] = (int8_t)action[k];
             }
             // ---- collectivecrossing.py:188 ---------------------------------------------------
             step += 1;
-            bool alive_prev[APL];
+            unsigned alive_prev[APL];  // 1 iff neither terminated nor truncated at step start
 #pragma unroll
-            for (int k = 0; k < APL; ++k) alive_prev[k] = avalid[k] && !(fl[k] & (CC_F_TERMINATED | CC_F_TRUNCATED));
+            for (int k = 0; k < APL; ++k) alive_prev[k] = (avalid[k] && (fl[k] & 6u) == 0u) ? 1u : 0u;
 
             // ---- collectivecrossing.py:197-202: ordered moves -------------------------------
             // cmp[k] = packed position of an ACTIVE agent, else a sentinel no target can equal;
@@ -445,14 +468,16 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             constexpr unsigned kNoMove = 0xFFFFFFFEu, kGhost = 0xFFFFFFFFu;
             unsigned cmp[APL];
 #pragma unroll
-            for (int k = 0; k < APL; ++k) cmp[k] = (env_ok && avalid[k] && (fl[k] & CC_F_ACTIVE)) ? pos[k] : kGhost;
+            for (int k = 0; k < APL; ++k) cmp[k] = (fl[k] & CC_F_ACTIVE) ? pos[k] : kGhost;
             auto make_request = [&](unsigned my_pos, int my_cell, int my_act, unsigned my_cmp) -> unsigned {
-                if (my_cmp == kGhost || (unsigned)my_act >= 4u) return kNoMove;        // :398, wait
+                // packed (dx << 8 | dy) mod 2^16 of actions 0..3 (actions.py:18-24)
+                const unsigned delta = (unsigned)((0xFFFFFF0000010100ull >> (16 * (my_act & 3))) & 0xffffull);
+                bool go = my_cmp != kGhost && (unsigned)my_act < 4u;                    // :398, wait
                 if (!geo_known) {                                                       // :509-534 via the static map
-                    const int t = my_cell + act_dx(my_act) + PW * act_dy(my_act);
-                    if (!((walk[t >> 5] >> (t & 31)) & 1u)) return kNoMove;
+                    const int t = my_cell + ((my_act & 1) ? PW : 1) * ((my_act & 2) ? -1 : 1);
+                    go = go && ((walk[(t >> 5) & 0x1ff] >> (t & 31)) & 1u);
                 }
-                return pack_pos(pos_x(my_pos) + act_dx(my_act), pos_y(my_pos) + act_dy(my_act));
+                return go ? ((my_pos + delta) & 0xffffu) : kNoMove;
             };
             if (p.order == nullptr) {
                 // every agent has an entry: :707-711 applies to all of them
@@ -484,20 +509,20 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             } else {
                 int ord[APL];
 #pragma unroll
-                for (int k = 0; k < APL; ++k) ord[k] = (env_ok && avalid[k]) ? (int)(p.order + row0)[off[k]] : -1;
+                for (int k = 0; k < APL; ++k) ord[k] = (env_ok && avalid[k]) ? (int)p.order[off[k]] : -1;
                 bool stop = !env_ok;
                 for (int k = 0; k < A; ++k) {
                     const int oi = (int)T.tshfl((unsigned)picki<APL>(ord, k >> TL_::LOG), k & (LPE - 1));
                     stop = stop || oi < 0;
                     bool live = !stop;
                     if (live && oi >= A) { errbits |= kErrInvalidAction; live = false; }  // :701-705
-                    const int ol = oi & (LPE - 1), os = oi >> TL_::LOG;
+                    const int ol = oi & (LPE - 1), os = (oi >> TL_::LOG) & (APL - 1);
                     const int my_act = picki<APL>(action, os);
                     const unsigned my_pos = pick<APL>(pos, os), my_cmp = pick<APL>(cmp, os);
                     const bool owner = live && T.li == ol;
                     if (owner && (unsigned)my_act > 4u) errbits |= kErrInvalidAction;   // :707-711
                     // the cell is recomputed: an agent listed twice has moved since the top of the step
-                    const int my_cell = (min(max(pos_y(my_pos), 0), p.H) + 1) * PW + min(max(pos_x(my_pos), 0), p.W) + 1;
+                    const int my_cell = (min((int)(my_pos & 0xffu), p.H + 1) + 1) * PW + min((int)(my_pos >> 8), p.W + 1) + 1;
                     unsigned rq = T.tshfl(make_request(my_pos, my_cell, my_act, my_cmp), ol);
                     if (!live) rq = kNoMove;
                     bool hit = false;
@@ -512,14 +537,14 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             }
 
             // ---- :210-212 deactivate arrivals; rewards; terminated; truncated --------------
-            bool arr[APL];
             bool lane_not_arr = false, lane_new_arr = false;
+            unsigned arr[APL];
 #pragma unroll
             for (int k = 0; k < APL; ++k) {
-                const int dest = aidx[k] < p.B ? p.YB : p.YE;          // :663-683 (y only)
-                arr[k] = avalid[k] && pos_y(pos[k]) == dest;
+                lookup(k);                                             // geometry of the post-move cell
+                arr[k] = avalid[k] ? (geo_f[k] >> 3) & 1u : 0u;        // :663-683 (y only)
                 const bool newly = env_ok && arr[k] && (fl[k] & CC_F_ACTIVE);
-                if (arr[k]) fl[k] &= ~(unsigned)CC_F_ACTIVE;           // types.py:46-51
+                fl[k] &= ~arr[k];                                      // types.py:46-51 (CC_F_ACTIVE == 1)
                 if (APL == 1) lane_new_arr = newly;
                 else st_arrivals += __popc(__ballot_sync(kFull, newly));   // counted warp-wide on every lane; lane 0's copy is used
                 lane_not_arr = lane_not_arr || (avalid[k] && !arr[k]);
@@ -533,40 +558,32 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             unsigned oflag[APL];
 #pragma unroll
             for (int k = 0; k < APL; ++k) {
-                const int x = pos_x(pos[k]), y = pos_y(pos[k]);
                 const bool boarding = aidx[k] < p.B;
-                float r = 0.f;
-                if (alive_prev[k]) {                                    // rewards.py:65-66 etc.
-                    switch (p.reward_kind) {
-                    case CC_REWARD_DEFAULT:                             // rewards.py:68-99
-                        if (arr[k]) r = p.rpf[0];                       // :78-79 and :88-89 (same parameter, sic)
-                        else if (boarding) {
-                            if (at_tram_door(p, x, y)) r = p.rpf[1];
-                            else if (in_tram_area(p, x, y)) r = p.rpf[2];
-                            else r = rtab_neg[abs(x - p.DC) + (p.D - y) + kRtabOff];    // :82-85
-                        } else {
-                            if (!in_tram_area(p, x, y)) r = p.rpf[2];
-                            else r = rtab_pos[abs(x - p.DC) + (y - p.D) + kRtabOff];    // :95-99 (positive, sic)
-                        }
-                        break;
-                    case CC_REWARD_SIMPLE_DISTANCE:                     // rewards.py:120-129
-                        r = rtab_neg[abs(y - (boarding ? p.YB : p.YE)) + kRtabOff];
-                        break;
-                    case CC_REWARD_BINARY: r = p.rpf[1]; break;         // rewards.py:152-159 (never goal_reward)
-                    default: r = p.rpf[0]; break;                       // rewards.py:179-182
-                    }
+                const unsigned f = geo_f[k];
+                float r;
+                switch (p.reward_kind) {
+                case CC_REWARD_DEFAULT: {                               // rewards.py:68-99
+                    const float dist = rtab[(boarding ? 0 : kRtabSize) + (int)((geo_u[k] >> 8) & 0x1ffu)];  // :82-85 / :95-99 (positive, sic)
+                    const float inside = boarding ? ((f & 2u) ? p.rpf[1] : p.rpf[2]) : dist;      // at door / in tram | exiting in tram
+                    const float outside = boarding ? dist : p.rpf[2];                              // exiting outside the tram: tram_area_reward (sic)
+                    r = (f & 8u) ? p.rpf[0] : ((f & (boarding ? 3u : 1u)) ? inside : outside);     // :78-79 and :88-89 (same parameter, sic)
+                    break;
                 }
+                case CC_REWARD_SIMPLE_DISTANCE: r = rtab[(int)((geo_u[k] >> 8) & 0x1ffu)]; break;   // rewards.py:120-129
+                case CC_REWARD_BINARY: r = p.rpf[1]; break;             // rewards.py:152-159 (never goal_reward)
+                default: r = p.rpf[0]; break;                           // rewards.py:179-182
+                }
+                r = alive_prev[k] ? r : 0.f;                            // rewards.py:65-66 etc.
                 rew[k] = r;
                 rsum_lane += r;
-                lane_alive |= alive_prev[k];
-                const bool tval = (p.terminated_kind == CC_TERM_ALL_AT_DESTINATION) ? all_arrived : arr[k];  // terminateds.py:56-60,82
-                const bool cval = alive_prev[k] && over_limit;          // truncateds.py:57-61
+                lane_alive |= alive_prev[k] != 0u;
+                const unsigned tval = (p.terminated_kind == CC_TERM_ALL_AT_DESTINATION) ? (unsigned)all_arrived : arr[k];  // terminateds.py:56-60,82
+                const unsigned cval = alive_prev[k] & (unsigned)over_limit;   // truncateds.py:57-61
                 // collectivecrossing.py:229-243: sticky flags; an entry is returned for agents that were
                 // alive at step start and for agents whose terminated flag flips now
-                const bool present = alive_prev[k] || (tval && !(fl[k] & CC_F_TERMINATED));
-                fl[k] |= (tval ? (unsigned)CC_F_TERMINATED : 0u) | (cval ? (unsigned)CC_F_TRUNCATED : 0u);
-                oflag[k] = (fl[k] & 7u) | (alive_prev[k] ? CC_O_ALIVE_PREV : 0u) | (tval ? CC_O_TERM_VALUE : 0u) |
-                           (cval ? CC_O_TRUNC_VALUE : 0u) | (present ? CC_O_OBS_PRESENT : 0u);
+                const unsigned present = alive_prev[k] | (tval & ~(fl[k] >> 1) & 1u);
+                fl[k] |= (tval << 1) | (cval << 2);
+                oflag[k] = (fl[k] & 7u) | (alive_prev[k] << 3) | (tval << 4) | (cval << 5) | (present << 6);
             }
             const bool any_alive = (__ballot_sync(kFull, lane_alive) & tile_bits) != 0u;
             const bool term_all = all_arrived;                          // :256 (terminateds holds every agent)
@@ -586,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
                 if (env_ok && avalid[k]) {
                     if (p.reward_f64) {
                         // single-env facade: the reference's float64 value itself
-                        const int x = pos_x(pos[k]), y = pos_y(pos[k]);
+                        const int x = (int)(pos[k] >> 8), y = (int)(pos[k] & 0xffu);
                         const bool boarding = aidx[k] < p.B;
                         double r = 0.0;
                         if (alive_prev[k]) {
@@ -601,14 +618,11 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
                             default: r = p.rp[0]; break;
                             }
                         }
-                        (reinterpret_cast<double *>(p.reward) + row0)[off[k]] = r;
-                    } else (reinterpret_cast<float *>(p.reward) + row0)[off[k]] = rew[k];
-                    (p.agent_flags + row0)[off[k]] = (uint8_t)oflag[k];
-                    if (p.agent_info) {                                 // :248-254
-                        const int x = pos_x(pos[k]), y = pos_y(pos[k]);
-                        (p.agent_info + row0)[off[k]] = (uint8_t)((in_tram_area(p, x, y) ? CC_I_IN_TRAM_AREA : 0) | (at_tram_door(p, x, y) ? CC_I_AT_DOOR : 0) |
-                                                                  ((fl[k] & CC_F_ACTIVE) ? CC_I_ACTIVE : 0) | (arr[k] ? CC_I_AT_DESTINATION : 0));
-                    }
+                        reinterpret_cast<double *>(p.reward)[off[k]] = r;
+                    } else reinterpret_cast<float *>(p.reward)[off[k]] = rew[k];
+                    p.agent_flags[off[k]] = (uint8_t)oflag[k];
+                    // :248-254: in_tram_area | at_door | active | at_destination
+                    if (p.agent_info) p.agent_info[off[k]] = (uint8_t)((geo_f[k] & 0xBu) | ((fl[k] & 1u) << 2));
                 }
             const bool leader = env_ok && T.li == 0;
             if (leader) st_rsum += (double)rsum;
@@ -628,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             need_reset = env_ok && done && p.auto_reset;
             if (need_reset) { eflags |= CC_E_WAS_RESET; ep_ret = 0.f; }
         }
-        if (MODE == kModeReset) need_reset = env_ok && (p.mask == nullptr || (p.mask + n0)[T.tile] != 0);
+        if (MODE == kModeReset) need_reset = env_ok && (p.mask == nullptr || p.mask[(int)n0 + T.tile] != 0);
 
         // ---- collectivecrossing.py:91-150 reset(): rejection-sampled placement ---------------
         // Agent i's k-th candidate is Philox(seed; genv, t, RESET, i<<16|k); it takes the first
@@ -711,14 +725,14 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
 #pragma unroll
             for (int k = 0; k < APL; ++k)
                 if (wr && avalid[k]) {
-                    (p.x + row0)[off[k]] = (int8_t)pos_x(pos[k]);
-                    (p.y + row0)[off[k]] = (int8_t)pos_y(pos[k]);
-                    (p.flags + row0)[off[k]] = (uint8_t)(fl[k] & 7u);
+                    p.x[off[k]] = (int8_t)(pos[k] >> 8);
+                    p.y[off[k]] = (int8_t)(pos[k] & 0xffu);
+                    p.flags[off[k]] = (uint8_t)(fl[k] & 7u);
                 }
             if (wr && T.li == 0) {
-                (p.step + n0)[T.tile] = step;
-                (p.ep_ret + n0)[T.tile] = ep_ret;
-                if (MODE == kModeStep) (p.env_flags + n0)[T.tile] = (uint8_t)eflags;
+                p.step[(int)n0 + T.tile] = step;
+                p.ep_ret[(int)n0 + T.tile] = ep_ret;
+                if (MODE == kModeStep) p.env_flags[(int)n0 + T.tile] = (uint8_t)eflags;
             }
         }
 
@@ -728,8 +742,8 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
 #pragma unroll
             for (int k = 0; k < APL; ++k)
                 if (avalid[k]) {
-                    tstage[2 * aidx[k]] = mk_pair<OT>(pos_x(pos[k]), pos_y(pos[k]));
-                    tstage[2 * aidx[k] + 1] = mk_pair<OT>(aidx[k] < p.B ? 0 : 1, (fl[k] & CC_F_ACTIVE) ? 1 : 0);
+                    tstage[2 * aidx[k]] = mk_pair<OT>((int)(int8_t)(pos[k] >> 8), (int)(int8_t)(pos[k] & 0xffu));
+                    tstage[2 * aidx[k] + 1] = mk_pair<OT>(aidx[k] < p.B ? 0 : 1, (int)(fl[k] & 1u));
                 }
             __syncwarp();
             OT *obs = reinterpret_cast<OT *>(p.obs);
@@ -737,49 +751,27 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             if (MODE == kModeReset) {
                 // only the envs that were reset get their rows rewritten
                 const unsigned tiles = __ballot_sync(kFull, need_reset);
-                if (!cached) {
-#pragma unroll
-                    for (int e = 0; e < EPW; ++e)
-                        if ((tiles >> (e * LPE)) & 1u)
-                            emit_obs_lut<OT>(obs, gp0 + (long long)e * p.pairs_per_env, p.pairs_per_env, lut + e * p.pairs_per_env, stage, T.lane);
-                }
-                if (kCanCache && cached) {
-                    // descriptors exist per whole chunk: store only the pairs of reset envs
-                    P2 *out = reinterpret_cast<P2 *>(obs) + gp0;
-#pragma unroll
-                    for (int q = 0; q < kDescRegs / 4; ++q) {
-                        const uint4 d4 = desc_sm[q * kThreads];
-                        const unsigned d[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int r = q * 4 + c;
-                            const int P = (T.lane + 32 * (r / RPV)) * PPV + 2 * (r % RPV);
-                            if (P + 1 < envs_here * p.pairs_per_env) {
-                                const int e0 = P / p.pairs_per_env, e1 = (P + 1) / p.pairs_per_env;
-                                if ((tiles >> (e0 * LPE)) & 1u) out[P] = stage[d[c] & 0xffffu];
-                                if ((tiles >> (e1 * LPE)) & 1u) out[P + 1] = stage[d[c] >> 16];
-                            }
-                        }
-                    }
-                }
+                P2 *out = reinterpret_cast<P2 *>(obs) + gp0;
+                for (int P = T.lane; P < envs_here * p.pairs_per_env; P += 32)
+                    if ((tiles >> ((P / p.pairs_per_env) * LPE)) & 1u) out[P] = stage[gather_index(p, P)];
             } else if (kCanCache && cached && envs_here == EPW) {
-                // whole, vector-aligned chunk: gather through the per-lane descriptors
+                // whole, vector-aligned chunk: each lane gathers its vectors through its descriptors
                 uint4 *outv = reinterpret_cast<uint4 *>(reinterpret_cast<P2 *>(obs) + gp0) + T.lane;
                 uint4 d4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int j = 0; j < kDescRegs / RPV; ++j) {
-                    if ((j * RPV) % 4 == 0) d4 = desc_sm[(j * RPV / 4) * kThreads];
-                    if (j < my_nvec) {
-                        const unsigned dd[4] = {d4.x, d4.y, d4.z, d4.w};
-                        union { uint4 u; P2 e[PPV]; } pk;
+                for (int j = 0; j < kDescWords / PPV; ++j) {
+                    union { uint4 u; P2 e[PPV]; } pk;
 #pragma unroll
-                        for (int h = 0; h < RPV; ++h) {
-                            const unsigned d = dd[(j * RPV + h) % 4];
-                            pk.e[2 * h] = stage[d & 0xffffu];
-                            pk.e[2 * h + 1] = stage[d >> 16];
-                        }
-                        __stcs(outv + 32 * j, pk.u);
+                    for (int h = 0; h < PPV; ++h) {
+                        const int w = j * PPV + h;
+                        if (w % 4 == 0) d4 = desc_sm[(w / 4) * kThreads];
+                        const unsigned a = (w % 4 == 0) ? d4.x : (w % 4 == 1) ? d4.y : (w % 4 == 2) ? d4.z : d4.w;
+                        P2 v;
+                        if (sizeof(P2) == 8) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(reinterpret_cast<float2 &>(v).x), "=f"(reinterpret_cast<float2 &>(v).y) : "r"(a));
+                        else { unsigned short hw; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hw) : "r"(a)); v = reinterpret_cast<P2 &>(hw); }
+                        pk.e[h] = v;
                     }
+                    if (j < my_nvec) __stcs(outv + 32 * j, pk.u);
                 }
             } else {
                 if (cached) {
