@@ -73,6 +73,7 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     p.YB = c.boarding_dest_y; p.YE = c.exiting_dest_y; p.B = c.num_boarding; p.A = h->A;
     p.max_steps = c.max_steps; p.reward_kind = c.reward_kind; p.terminated_kind = c.terminated_kind;
     for (int i = 0; i < 4; ++i) { p.rp[i] = c.reward_params[i]; p.rpf[i] = (float)c.reward_params[i]; }
+    p.reward_category_mask = c.reward_kind == CC_REWARD_DEFAULT ? 0xFu : 0u;
     p.n_envs = h->n_envs; p.genv_offset = (unsigned long long)h->genv_offset; p.seed = h->seed; p.t = (unsigned)h->t;
     p.x = h->x; p.y = h->y; p.flags = h->flags; p.step = h->step; p.ep_ret = h->ep_ret;
     p.stats = h->stats; p.err = h->err;
@@ -83,20 +84,12 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     p.walk_words = ((c.width + 3) * (c.height + 3) + 31) / 32;
     const int pair_bytes = obs_dtype == CC_OBS_FP32 ? 8 : 2;
     int off = round_up(p.lut_entries * 2, 16);
-    p.off_walk = off;
-    off += round_up(p.walk_words * 4, 16);
-    p.off_geo = off;   // xt[W+3], yt[2][H+3] (uint32), act_tab[kPolicyRows*16] (bytes)
-    off += round_up(((c.width + 3) + 2 * (c.height + 3)) * 4 + ccb::kPolicyRows * 16, 16);
     p.off_stage = off;
     off += round_up(ccb::kWarpsPerCta * p.stage_pairs * pair_bytes, 16);
     p.off_bitmap = off;
     off += needs_bitmap ? round_up(ccb::kWarpsPerCta * h->epw * p.walk_words * 4, 16) : 0;
-    p.off_red = off;
-    off += ccb::kWarpsPerCta * ccb::kStCount * 8;
     p.off_desc = off;
     off += (obs_dtype != CC_OBS_NONE && h->lpe <= 16) ? ccb::kDescWords * 4 * ccb::kThreads : 0;
-    p.off_rtab = off;
-    off += 2 * ccb::kRtabSize * 4;
     p.smem_total = off;
     p.n_groups = (h->n_envs + h->epw - 1) / h->epw;
 }
@@ -106,8 +99,9 @@ template <int LPE, int APL, int OBS, int MODE>
 int launch_t(cc_handle *h, const KParams &p, cudaStream_t s) {
     auto kern = ccb::cc_kernel<LPE, APL, OBS, MODE>;
     const int smem = smem_bytes(p);
-    if (smem > 227 * 1024) return fail(CC_ERR_UNSUPPORTED, "configuration needs %d bytes of shared memory", smem);
-    if (smem > 48 * 1024) CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (smem > 218 * 1024) return fail(CC_ERR_UNSUPPORTED, "configuration needs %d bytes of shared memory", smem);
+    // the kernels also hold ~8 KB of static shared memory: opt in as soon as the sum can pass the 48 KB default
+    if (smem > 36 * 1024) CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
     CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ccb::kThreads, smem));
     if (per_sm < 1) return fail(CC_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %d)", smem);
@@ -195,7 +189,7 @@ int cc_create(const cc_config *cfg, int64_t n_envs, int device, int64_t global_e
     if (n_envs * (int64_t)A >= (int64_t)1 << 31) return fail(CC_ERR_UNSUPPORTED, "n_envs * agents must stay below 2^31 per handle (32-bit slot indices)");
     const int32_t geo[] = {cfg->width, cfg->height, cfg->division_y, cfg->tram_left, cfg->tram_right, cfg->door_left, cfg->door_right, cfg->boarding_dest_y, cfg->exiting_dest_y};
     for (int32_t v : geo)
-        if (v < -1 || v > 126) return fail(CC_ERR_UNSUPPORTED, "geometry value %d does not fit the int8 lattice", v);
+        if (v < -1 || v > ccb::kMaxGeom) return fail(CC_ERR_UNSUPPORTED, "geometry value %d is outside the supported lattice (0..%d)", v, ccb::kMaxGeom);
     if (cfg->width < 1 || cfg->height < 1) return fail(CC_ERR_INVALID_ARG, "width and height must be positive");
     if (cfg->reward_kind < 0 || cfg->reward_kind > CC_REWARD_CONSTANT_NEGATIVE) return fail(CC_ERR_INVALID_ARG, "unknown reward_kind %d", cfg->reward_kind);
     if (cfg->terminated_kind < 0 || cfg->terminated_kind > CC_TERM_ALL_AT_DESTINATION) return fail(CC_ERR_INVALID_ARG, "unknown terminated_kind %d", cfg->terminated_kind);

@@ -16,7 +16,7 @@
 #include "../../include/ccb200.h"
 
 #ifndef CCB_MIN_BLOCKS
-#define CCB_MIN_BLOCKS 5  // resident CTAs per SM the register allocator must allow (A/B in DESIGN.md §6)
+#define CCB_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must allow (A/B in DESIGN.md §6)
 #endif
 
 namespace ccb {
@@ -60,8 +60,9 @@ struct KParams {
     int lut_entries;     // EPW * A * R
     int stage_pairs;     // 3 + EPW * 2A (per warp)
     int walk_words;      // words of one padded-lattice bitmap: ceil((W+3)(H+3)/32)
-    int off_walk, off_geo, off_stage, off_bitmap, off_red, off_desc, off_rtab;
+    int off_stage, off_bitmap, off_desc;
     float rpf[4];        // reward parameters rounded to float32 once
+    unsigned reward_category_mask;  // 0xF for the default reward (category overrides apply), else 0
     long long n_groups;
     int smem_total;
 };
@@ -213,6 +214,9 @@ constexpr int kDescWords = 24;                 // cached gather descriptors per 
 constexpr int kDescPairs = 32 * kDescWords;    // = 768 output pairs per warp chunk
 constexpr int kRtabSize = 400;                 // reward-table index = |x-DC| (<= 128) + biased y distance (< 256)
 constexpr int kYBias = 128;
+constexpr int kMaxGeom = 120;                  // largest width / height the tables are sized for (reference: 100)
+constexpr int kMaxPad = kMaxGeom + 4;          // padded lattice side
+constexpr int kMaxWalkWords = 512;             // >= ceil(kMaxPad^2 / 32) = 481; a power of two so garbage indices can be masked
 constexpr int kNumYClass = 5;                  // far / door level / beyond: up, down, at destination
 constexpr int kPolicyRows = 2 * kNumYClass * 3;  // (type, y class, x class)
 
@@ -279,11 +283,13 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
     const int warp = threadIdx.x >> 5;
     const int A = p.A;
     const int PW = p.W + 3, PH = p.H + 3;  // lattice padded by one ring: x in [-1, W+1] -> column x+1
+    // fixed-size tables live in STATIC shared memory: their addresses are immediates, nothing has to
+    // be kept in (or rematerialised into) registers to reach them
+    __shared__ unsigned xt[kMaxPad], yt[2 * kMaxPad], walk[kMaxWalkWords];
+    __shared__ float rtab[2 * kRtabSize];
+    __shared__ uint8_t act_tab[kPolicyRows * 16];
+    __shared__ unsigned long long red_all[kWarpsPerCta * kStCount];
     uint16_t *lut = reinterpret_cast<uint16_t *>(smem);
-    unsigned *walk = reinterpret_cast<unsigned *>(smem + p.off_walk);
-    unsigned *xt = reinterpret_cast<unsigned *>(smem + p.off_geo), *yt = xt + PW;
-    uint8_t *act_tab = reinterpret_cast<uint8_t *>(yt + 2 * PH);
-    float *rtab = reinterpret_cast<float *>(smem + p.off_rtab);   // [2][kRtabSize]
     P2 *stage = reinterpret_cast<P2 *>(smem + p.off_stage) + warp * p.stage_pairs;
     unsigned *blocked = reinterpret_cast<unsigned *>(smem + p.off_bitmap) + (warp * EPW + T.tile) * p.walk_words;
 
@@ -314,18 +320,21 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
         if (T.lane == 0) { stage[0] = mk_pair<OT>(p.DC, p.D); stage[1] = mk_pair<OT>(p.DL, p.DR); stage[2] = mk_pair<OT>(-1, -1); }
     }
     for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
-    for (int i = threadIdx.x; i < 2 * PH; i += blockDim.x) yt[i] = make_yt(p, i / PH, i % PH - 1);
+    for (int i = threadIdx.x; i < 2 * PH; i += blockDim.x) yt[(i / PH) * kMaxPad + i % PH] = make_yt(p, i / PH, i % PH - 1);
     if (kHasPolicy)
         for (int i = threadIdx.x; i < kPolicyRows * 16; i += blockDim.x) act_tab[i] = (uint8_t)greedy_decision(i >> 4, (unsigned)i & 15u);
     // distance rewards: entry k holds float((double)(-d) * f) (boarding / simple distance) or
     // float((double)d * f) (exiting, default reward) for d = k - kYBias: the reference's float64 product
     // (rewards.py:85,99,127) rounded once — no FP64 in the loop
-    if (kMoves && p.reward_kind <= CC_REWARD_SIMPLE_DISTANCE) {
+    if (kMoves) {
         const double f = p.reward_kind == CC_REWARD_DEFAULT ? p.rp[3] : p.rp[0];
         for (int i = threadIdx.x; i < 2 * kRtabSize; i += blockDim.x) {
             const int type = i / kRtabSize, d = i % kRtabSize - kYBias;
             const bool negate = type == 0 || p.reward_kind == CC_REWARD_SIMPLE_DISTANCE;
-            rtab[i] = (float)((double)(negate ? -d : d) * f);
+            float v = (float)((double)(negate ? -d : d) * f);
+            if (p.reward_kind == CC_REWARD_BINARY) v = p.rpf[1];                  // rewards.py:152-159 (never goal_reward)
+            if (p.reward_kind == CC_REWARD_CONSTANT_NEGATIVE) v = p.rpf[0];       // rewards.py:179-182
+            rtab[i] = v;
         }
     }
     // static map of walkable lattice points (collectivecrossing.py:509-534), one bit per point of
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
     }
     // statistics: arrivals and the reward sum change every step and stay in registers; the
     // episode-end sums are updated on the (rare) step an episode ends, in the warp's smem slot
-    unsigned long long *red = reinterpret_cast<unsigned long long *>(smem + p.off_red) + warp * kStCount;
+    unsigned long long *red = red_all + warp * kStCount;
     if (kMoves && T.lane < kStCount) red[T.lane] = 0ull;
     __syncthreads();
     unsigned st_arrivals = 0;
@@ -348,14 +357,15 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
     int errbits = 0;
 
     // ---- per-lane constants ---------------------------------------------------------------------------
-    int aidx[APL], aload[APL], ytoff[APL];
+    int aidx[APL], aload[APL], ytoff[APL], rtoff[APL];
     bool avalid[APL];
 #pragma unroll
     for (int k = 0; k < APL; ++k) {
         aidx[k] = T.li + k * LPE;
         avalid[k] = aidx[k] < A;
         aload[k] = T.tile * A + min(aidx[k], A - 1);   // lanes beyond A re-read agent A-1 (never stored)
-        ytoff[k] = aidx[k] < p.B ? 0 : PH;              // row of yt for this agent's type
+        ytoff[k] = aidx[k] < p.B ? 0 : kMaxPad;         // row of yt for this agent's type
+        rtoff[k] = aidx[k] < p.B ? 0 : kRtabSize;       // half of rtab for this agent's type
     }
     const unsigned tile_bits = TL_::MASK << T.tshift;
     const int group_stride = EPW * A;
@@ -465,19 +475,21 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             // cmp[k] = packed position of an ACTIVE agent, else a sentinel no target can equal;
             // a request is the packed target cell, or kNoMove.  A mover's target never equals its
             // own cell, so the occupancy ballot (:536-541) needs no self-exclusion.
-            constexpr unsigned kNoMove = 0xFFFFFFFEu, kGhost = 0xFFFFFFFFu;
+            // A request that must not move is the owner's own cmp value: the owner (or every ghost) hits it
+            // in the ballot, so it can never be committed and needs no separate test.
+            constexpr unsigned kGhost = 0xFFFFFFFFu;
             unsigned cmp[APL];
 #pragma unroll
             for (int k = 0; k < APL; ++k) cmp[k] = (fl[k] & CC_F_ACTIVE) ? pos[k] : kGhost;
-            auto make_request = [&](unsigned my_pos, int my_cell, int my_act, unsigned my_cmp) -> unsigned {
+            auto make_request = [&](int my_cell, int my_act, unsigned my_cmp) -> unsigned {
                 // packed (dx << 8 | dy) mod 2^16 of actions 0..3 (actions.py:18-24)
                 const unsigned delta = (unsigned)((0xFFFFFF0000010100ull >> (16 * (my_act & 3))) & 0xffffull);
                 bool go = my_cmp != kGhost && (unsigned)my_act < 4u;                    // :398, wait
                 if (!geo_known) {                                                       // :509-534 via the static map
                     const int t = my_cell + ((my_act & 1) ? PW : 1) * ((my_act & 2) ? -1 : 1);
-                    go = go && ((walk[(t >> 5) & 0x1ff] >> (t & 31)) & 1u);
+                    go = go && ((walk[(t >> 5) & 0x1ff] >> (t & 31)) & 1u);  // (mask: garbage positions stay inside the table)
                 }
-                return go ? ((my_pos + delta) & 0xffffu) : kNoMove;
+                return go ? ((my_cmp + delta) & 0xffffu) : my_cmp;
             };
             if (p.order == nullptr) {
                 // every agent has an entry: :707-711 applies to all of them
@@ -485,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
 #pragma unroll
                 for (int k = 0; k < APL; ++k) {
                     if (env_ok && avalid[k] && (unsigned)action[k] > 4u) errbits |= kErrInvalidAction;
-                    req[k] = make_request(pos[k], cell[k], action[k], cmp[k]);
+                    req[k] = make_request(cell[k], action[k], cmp[k]);
                 }
                 auto turn = [&](const int s, const int l) {
                     const unsigned rq = T.tshfl(req[s], l);
@@ -493,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
 #pragma unroll
                     for (int k = 0; k < APL; ++k) hit |= cmp[k] == rq;
                     const unsigned occ = __ballot_sync(kFull, hit) & tile_bits;
-                    if (T.li == l && rq != kNoMove && !occ) { pos[s] = rq; cmp[s] = rq; }   // :406-408
+                    if (T.li == l && !occ) cmp[s] = rq;                                     // :406-408
                 };
                 if (APL == 1 && A == LPE) {
 #pragma unroll
@@ -518,23 +530,24 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
                     if (live && oi >= A) { errbits |= kErrInvalidAction; live = false; }  // :701-705
                     const int ol = oi & (LPE - 1), os = (oi >> TL_::LOG) & (APL - 1);
                     const int my_act = picki<APL>(action, os);
-                    const unsigned my_pos = pick<APL>(pos, os), my_cmp = pick<APL>(cmp, os);
+                    const unsigned my_cmp = pick<APL>(cmp, os);
                     const bool owner = live && T.li == ol;
                     if (owner && (unsigned)my_act > 4u) errbits |= kErrInvalidAction;   // :707-711
                     // the cell is recomputed: an agent listed twice has moved since the top of the step
-                    const int my_cell = (min((int)(my_pos & 0xffu), p.H + 1) + 1) * PW + min((int)(my_pos >> 8), p.W + 1) + 1;
-                    unsigned rq = T.tshfl(make_request(my_pos, my_cell, my_act, my_cmp), ol);
-                    if (!live) rq = kNoMove;
-                    bool hit = false;
+                    const int my_cell = (min((int)(my_cmp & 0xffu), p.H + 1) + 1) * PW + min((int)((my_cmp >> 8) & 0xffu), p.W + 1) + 1;
+                    unsigned rq = T.tshfl(make_request(my_cell, my_act, my_cmp), ol);
+                    bool hit = !live;   // a dead turn hits itself everywhere
 #pragma unroll
                     for (int s = 0; s < APL; ++s) hit |= cmp[s] == rq;
                     const unsigned occ = __ballot_sync(kFull, hit) & tile_bits;
-                    if (owner && rq != kNoMove && !occ) {
+                    if (owner && !occ) {
 #pragma unroll
-                        for (int s = 0; s < APL; ++s) if (s == os) { pos[s] = rq; cmp[s] = rq; }
+                        for (int s = 0; s < APL; ++s) if (s == os) cmp[s] = rq;
                     }
                 }
             }
+#pragma unroll
+            for (int k = 0; k < APL; ++k) pos[k] = (fl[k] & CC_F_ACTIVE) ? cmp[k] : pos[k];   // ghosts never move
 
             // ---- :210-212 deactivate arrivals; rewards; terminated; truncated --------------
             bool lane_not_arr = false, lane_new_arr = false;
@@ -558,21 +571,16 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             unsigned oflag[APL];
 #pragma unroll
             for (int k = 0; k < APL; ++k) {
-                const bool boarding = aidx[k] < p.B;
+                // One path for the four reward functions: the distance table holds the per-kind value
+                // (a constant for binary / constant_negative), and the DefaultReward categories
+                // (rewards.py:78-99) override it where their mask bits are set (masks are 0 for the others).
                 const unsigned f = geo_f[k];
-                float r;
-                switch (p.reward_kind) {
-                case CC_REWARD_DEFAULT: {                               // rewards.py:68-99
-                    const float dist = rtab[(boarding ? 0 : kRtabSize) + (int)((geo_u[k] >> 8) & 0x1ffu)];  // :82-85 / :95-99 (positive, sic)
-                    const float inside = boarding ? ((f & 2u) ? p.rpf[1] : p.rpf[2]) : dist;      // at door / in tram | exiting in tram
-                    const float outside = boarding ? dist : p.rpf[2];                              // exiting outside the tram: tram_area_reward (sic)
-                    r = (f & 8u) ? p.rpf[0] : ((f & (boarding ? 3u : 1u)) ? inside : outside);     // :78-79 and :88-89 (same parameter, sic)
-                    break;
-                }
-                case CC_REWARD_SIMPLE_DISTANCE: r = rtab[(int)((geo_u[k] >> 8) & 0x1ffu)]; break;   // rewards.py:120-129
-                case CC_REWARD_BINARY: r = p.rpf[1]; break;             // rewards.py:152-159 (never goal_reward)
-                default: r = p.rpf[0]; break;                           // rewards.py:179-182
-                }
+                float r = rtab[rtoff[k] + (int)((geo_u[k] >> 8) & 0x1ffu)];       // :82-85 / :95-99 (positive, sic) / :127
+                const bool boarding = aidx[k] < p.B;
+                const float special = boarding ? ((f & 2u) ? p.rpf[1] : p.rpf[2]) : p.rpf[2];  // door / tram area | exiting outside (sic)
+                const unsigned in_special = boarding ? (f & 3u) : ((f & 1u) ^ 1u);
+                r = (in_special & p.reward_category_mask) ? special : r;
+                r = (f & 8u & p.reward_category_mask) ? p.rpf[0] : r;              // :78-79 and :88-89 (same parameter, sic)
                 r = alive_prev[k] ? r : 0.f;                            // rewards.py:65-66 etc.
                 rew[k] = r;
                 rsum_lane += r;
@@ -757,21 +765,24 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             } else if (kCanCache && cached && envs_here == EPW) {
                 // whole, vector-aligned chunk: each lane gathers its vectors through its descriptors
                 uint4 *outv = reinterpret_cast<uint4 *>(reinterpret_cast<P2 *>(obs) + gp0) + T.lane;
+                const int nvec = chunk_pairs / PPV, nfull = nvec >> 5;   // rows of 32 vectors all lanes store
                 uint4 d4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int j = 0; j < kDescWords / PPV; ++j) {
-                    union { uint4 u; P2 e[PPV]; } pk;
+                    if (j * 32 < nvec) {                                  // uniform
+                        union { uint4 u; P2 e[PPV]; } pk;
 #pragma unroll
-                    for (int h = 0; h < PPV; ++h) {
-                        const int w = j * PPV + h;
-                        if (w % 4 == 0) d4 = desc_sm[(w / 4) * kThreads];
-                        const unsigned a = (w % 4 == 0) ? d4.x : (w % 4 == 1) ? d4.y : (w % 4 == 2) ? d4.z : d4.w;
-                        P2 v;
-                        if (sizeof(P2) == 8) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(reinterpret_cast<float2 &>(v).x), "=f"(reinterpret_cast<float2 &>(v).y) : "r"(a));
-                        else { unsigned short hw; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hw) : "r"(a)); v = reinterpret_cast<P2 &>(hw); }
-                        pk.e[h] = v;
+                        for (int h = 0; h < PPV; ++h) {
+                            const int w = j * PPV + h;
+                            if (w % 4 == 0) d4 = desc_sm[(w / 4) * kThreads];
+                            const unsigned a = (w % 4 == 0) ? d4.x : (w % 4 == 1) ? d4.y : (w % 4 == 2) ? d4.z : d4.w;
+                            P2 v;
+                            if (sizeof(P2) == 8) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(reinterpret_cast<float2 &>(v).x), "=f"(reinterpret_cast<float2 &>(v).y) : "r"(a));
+                            else { unsigned short hw; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hw) : "r"(a)); v = reinterpret_cast<P2 &>(hw); }
+                            pk.e[h] = v;
+                        }
+                        if (j < nfull || T.lane < (nvec & 31)) __stcs(outv + 32 * j, pk.u);
                     }
-                    if (j < my_nvec) __stcs(outv + 32 * j, pk.u);
                 }
             } else {
                 if (cached) {
@@ -798,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             red[kStRewardSum] = (unsigned long long)__double_as_longlong(rs);
         }
         __syncthreads();
-        const unsigned long long *all = reinterpret_cast<unsigned long long *>(smem + p.off_red);
+        const unsigned long long *all = red_all;
         if (threadIdx.x >= 1 && threadIdx.x < 6) {
             unsigned long long v = 0;
             for (int w = 0; w < kWarpsPerCta; ++w) v += all[w * kStCount + threadIdx.x];

@@ -57,8 +57,8 @@ def lower_config(config: Any) -> _abi.CCConfig:
         raise ValueError(f"the B200 kernels support 1..{_abi.MAX_AGENTS} agents per env, got {n_agents}")
     for name in ("width", "height", "division_y", "tram_left", "tram_right", "door_left", "door_right",
                  "boarding_dest_y", "exiting_dest_y"):
-        if not -1 <= getattr(out, name) <= 126:
-            raise ValueError(f"{name}={getattr(out, name)} does not fit the int8 lattice of the device state")
+        if not -1 <= getattr(out, name) <= 120:
+            raise ValueError(f"{name}={getattr(out, name)} is outside the lattice the device tables support (0..120)")
     return out
 
 
