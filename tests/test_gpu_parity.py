@@ -332,3 +332,87 @@ def test_policy_actions_kernel_matches_step_policy():
         else:
             assert torch.equal(standalone, applied)
         env.load_state(snap)
+
+
+# ---- random geometries: every table the kernel builds (walkable map, x/y words, greedy rows, reward
+# tables) against the oracle's straight-line arithmetic -----------------------------------------------
+def _random_config(rng):
+    from cases import REWARDS, TERMS, unchecked
+    from collectivecrossing_b200.truncated_configs import MaxStepsTruncatedConfig
+
+    while True:
+        W, H = int(rng.integers(3, 60)), int(rng.integers(3, 40))
+        D, L = int(rng.integers(1, H)), int(rng.integers(2, W + 1))
+        dl = int(rng.integers(0, L))
+        dr = int(rng.integers(dl, L))
+        B, E = int(rng.integers(0, 12)), int(rng.integers(0, 9))
+        half = L // 2
+        tl, tr = W // 2 - half, W // 2 + half
+        inside = max(0, tr - tl - 1)
+        door = max(0, (tl + dr) - (tl + dl) - 1)
+        free_tram = inside * (H - D - 1) + door
+        free_wait = W * D - (dr - dl + 1)
+        if B + E == 0 or E > free_tram // 2 or B > free_wait // 2:
+            continue
+        reward = list(REWARDS)[int(rng.integers(0, 4))]
+        kw = {"default": dict(distance_penalty_factor=float(rng.choice([0.1, 0.37, 1.5])), tram_door_reward=7.5),
+              "simple_distance": dict(distance_penalty_factor=0.3), "binary": dict(no_goal_reward=-0.25),
+              "constant_negative": dict(step_penalty=-1.75)}[reward]
+        return unchecked(
+            width=W, height=H, division_y=D, tram_door_left=dl, tram_door_right=dr, tram_length=L,
+            num_boarding_agents=B, num_exiting_agents=E, exiting_destination_area_y=int(rng.integers(0, D)),
+            boarding_destination_area_y=int(rng.integers(D, H + 1)), reward_config=REWARDS[reward](**kw),
+            terminated_config=list(TERMS.values())[int(rng.integers(0, 2))](),
+            truncated_config=MaxStepsTruncatedConfig(max_steps=int(rng.integers(1, 50))))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_geometries_match_oracle(seed):
+    import oracle
+
+    rng = np.random.default_rng(1000 + seed)
+    cfg = _random_config(rng)
+    low = lower_config(cfg)
+    n = int(rng.integers(1, 200))
+    x, y, f, s = random_states(cfg, n, rng)
+    for policy in ("greedy", "waiting", "random"):
+        env = make_env(cfg, n, seed=seed, global_env_offset=3, obs_dtype="int8", auto_reset=True, with_info=True)
+        orc = oracle.OracleEnvs(low, n, seed=seed, global_env_offset=3)
+        env.set_state(*(torch.from_numpy(v).cuda() for v in (x, y, f, s)))
+        orc.set_state(x, y, f, s)
+        for t in range(40):
+            out = env.step(policy=policy)
+            res = orc.step(policy=policy, auto_reset=True, obs_dtype=_abi.OBS_INT8)
+            _compare_step(env, orc, res, out, f"seed{seed}/{policy}/t={t} cfg={cfg.width}x{cfg.height} A={low.num_agents}", np.int8)
+        env.check_error()
+        env.close()
+
+
+def test_impossible_placement_terminates_with_reset_stuck():
+    """A tram with no interior cell: the reference's reset() would spin forever; the kernel stops after
+    the attempt cap, places the agent on its last candidate (like the oracle) and reports the error."""
+    import oracle
+    from cases import unchecked
+
+    cfg = unchecked(width=6, height=4, division_y=2, tram_door_left=0, tram_door_right=0, tram_length=1,
+                    num_boarding_agents=1, num_exiting_agents=1, exiting_destination_area_y=0, boarding_destination_area_y=4)
+    env = make_env(cfg, 5, seed=1, obs_dtype="int8")
+    orc = oracle.OracleEnvs(lower_config(cfg), 5, seed=1)
+    env.reset()
+    with pytest.raises(RuntimeError):
+        orc.reset()
+    assert np.array_equal(env.x.cpu().numpy(), orc.x) and np.array_equal(env.y.cpu().numpy(), orc.y)
+    with pytest.raises(Exception, match="no free valid cell"):
+        env.check_error()
+
+
+def test_rollout_equals_repeated_steps():
+    cfg = readme_config(max_steps=40)
+    a = make_env(cfg, 999, seed=4, obs_dtype="int8")
+    b = make_env(cfg, 999, seed=4, obs_dtype="int8")
+    a.reset(); b.reset()
+    a.rollout(57, policy="greedy")
+    for _ in range(57):
+        out = b.step(policy="greedy")
+    assert torch.equal(a.x, b.x) and torch.equal(a.flags, b.flags) and torch.equal(a.obs, out.obs)
+    assert a.stats() == b.stats()
