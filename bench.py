@@ -17,9 +17,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 from pathlib import Path
 
@@ -68,37 +66,76 @@ def config_dict(args, n_total):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every few milliseconds on a host thread (the
+    timed region lasts tens of milliseconds, far less than one `nvidia-smi -lms` period).  Only
+    the samples taken between mark_begin() and mark_end() — the timed region — are summarised."""
 
-    def __init__(self, gpu_index: int):
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.proc = None
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTED = {"sw_power_cap": 0x4}
+
+    def __init__(self, gpu_index: int, period_s: float = 0.002):
+        import threading
+
+        self.rows, self.t_begin, self.t_end, self.err = [], None, None, None
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=self.tmp, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it holds plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[gpu_index]) if gpu_index < len(ids) else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # noqa: BLE001 - no NVML, no clocks
+            self.err, self.thread = f"NVML unavailable: {exc}", None
+            return
+        self.period = period_s
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                try:
+                    power = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                except Exception:  # noqa: BLE001
+                    power = float("nan")
+                self.rows.append((time.perf_counter(), float(mhz), int(reasons), power))
+            except Exception as exc:  # noqa: BLE001
+                self.err = str(exc)
+                return
+            self._stop.wait(self.period)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.tmp.flush()
-        rows = [r.split(",") for r in Path(self.tmp.name).read_text().strip().splitlines() if r.count(",") >= 8]
-        os.unlink(self.tmp.name)
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        t0, t1 = self.t_begin or 0.0, self.t_end or float("inf")
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not rows:   # region shorter than one sample period: the nearest samples on either side
+            rows = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:2]
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any("Active" == r[5 + k].strip() for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
-                "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [self.err or "no samples"]}
+        sm = sorted(r[1] for r in rows)
+        seen = 0
+        for r in rows:
+            seen |= r[2]
+        reasons = [nm for nm, bit in {**self.BAD, **self.NOTED}.items() if seen & bit]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "samples": len(rows),
+                "power_w_max": max(r[3] for r in rows), "reasons": reasons, "source": "NVML, samples inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,7 +287,11 @@ def run_ours(args):
     launches0 = env.launch_count
 
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark_begin()
     ms = time_steps(env, torch, dist, args, args.steps, args.policy, world)
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
     launches = env.launch_count - launches0
     env.check_error()

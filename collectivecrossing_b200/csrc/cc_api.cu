@@ -80,7 +80,7 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     p.R = 3 + 2 * h->A;
     p.pairs_per_env = h->A * p.R;
     p.lut_entries = obs_dtype == CC_OBS_NONE ? 0 : h->epw * p.pairs_per_env;
-    p.stage_pairs = obs_dtype == CC_OBS_NONE ? 0 : round_up(3 + h->epw * 2 * h->A, 8);
+    p.stage_pairs = obs_dtype == CC_OBS_NONE ? 0 : round_up(h->epw * (2 * h->A + 4), 8);  // one row template per env
     p.walk_words = ((c.width + 3) * (c.height + 3) + 31) / 32;
     const int pair_bytes = obs_dtype == CC_OBS_FP32 ? 8 : 2;
     int off = round_up(p.lut_entries * 2, 16);

@@ -15,6 +15,9 @@
 
 #include "../../include/ccb200.h"
 
+#ifndef CCB_PREFETCH
+#define CCB_PREFETCH 0   // software prefetch of the next group's record (measured: no gain)
+#endif
 #ifndef CCB_MIN_BLOCKS
 #define CCB_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must allow (A/B in DESIGN.md §6)
 #endif
@@ -167,21 +170,21 @@ struct Tile {
 // Observation expansion.
 // Row i of an env is  [P_i, K1, K2, S_0a, S_0b, S_1a, S_1b, ...] with S_ia,S_ib replaced by M
 // (observations.py:62-94), in PAIR units: P_i=(x_i,y_i) K1=(DC,D) K2=(DL,DR) S_ja=(x_j,y_j)
-// S_jb=(type_j,active_j) M=(-1,-1).  A warp stages [K1, K2, M, then per tile 2A pairs S_*] in
-// shared memory and gathers output pairs from there.  gather_index() maps a pair of the warp's
-// output chunk to its stage pair; it is loop-invariant, so it is evaluated once per kernel:
-// into per-lane registers when the chunk is small (A <= 13), else into a shared-memory LUT.
+// S_jb=(type_j,active_j) M=(-1,-1).  A warp stages one row TEMPLATE per env in shared memory,
+//      T_e = [unused, K1, K2, S_0a, S_0b, ..., S_(A-1)b, M]          (2A+4 pairs)
+// so output pair q of any row reads T_e[q] — consecutive output pairs read consecutive addresses, which
+// keeps the gather free of bank conflicts — except q = 0 (reads S_ia = T_e[3+2i]) and the own block
+// (reads M = T_e[2A+3]).  gather_index() is loop-invariant: it is evaluated once per kernel into
+// per-lane descriptors when the chunk is small (A <= 13), else into a shared-memory LUT.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int gather_index(const KParams &p, int P) {
     const int A = p.A, R = p.R, ppe = p.pairs_per_env;
     int tile = P / ppe, q0 = P - tile * ppe;
     int i = q0 / R, q = q0 - i * R;
-    int base = 3 + tile * 2 * A;
-    if (q == 0) return base + 2 * i;
-    if (q == 1) return 0;
-    if (q == 2) return 1;
-    int j = (q - 3) >> 1, h = (q - 3) & 1;
-    return (j == i) ? 2 : base + 2 * j + h;
+    int base = tile * (2 * A + 4);
+    if (q == 0) return base + 3 + 2 * i;
+    if (q >= 3 && ((q - 3) >> 1) == i) return base + 2 * A + 3;
+    return base + q;
 }
 
 // generic path: `count` pairs starting at global pair index gp0, 16-byte vectors wherever a whole
@@ -295,29 +298,33 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
 
     // ---- once per CTA: gather descriptors / LUT, geometry tables -----------------------------------
     const int chunk_pairs = EPW * p.pairs_per_env;
-    const bool cached = kCanCache && chunk_pairs <= kDescPairs && (chunk_pairs % PPV) == 0;
+    constexpr bool kPairwise = false;             // (8-byte pair-wise stores measured slower than 16-byte vectors: 0.308 vs 0.276 ms)
+    const bool cached = kCanCache && chunk_pairs <= kDescPairs && (kPairwise || (chunk_pairs % PPV) == 0);
     uint4 *desc_sm = reinterpret_cast<uint4 *>(smem + p.off_desc) + threadIdx.x;  // [kDescWords/4][kThreads], conflict-free
-    int my_nvec = 0;  // vectors of a whole chunk this lane stores
     if (kHasObs) {
         if (cached) {
-            // descriptor = shared-memory byte address of the stage pair feeding one output pair
-            my_nvec = max(0, (chunk_pairs / PPV - T.lane + 31) / 32);
-            const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(stage);
+            // descriptor = byte offset (from the dynamic shared-memory base) of the template pair that
+            // feeds one output pair.  fp32: word w serves output pair lane + 32 w (stored pair-wise);
+            // int8: word w serves pair w % 8 of the lane's 16-byte vector number w / 8.
+            const unsigned stage_off = (unsigned)(reinterpret_cast<unsigned char *>(stage) - smem);
 #pragma unroll
             for (int q = 0; q < kDescWords / 4; ++q) {
                 unsigned d[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int w = q * 4 + c;
-                    const int P = (T.lane + 32 * (w / PPV)) * PPV + (w % PPV);
-                    d[c] = stage_addr + (unsigned)sizeof(P2) * (unsigned)(P < chunk_pairs ? gather_index(p, P) : 0);
+                    const int P = kPairwise ? T.lane + 32 * w : (T.lane + 32 * (w / PPV)) * PPV + (w % PPV);
+                    d[c] = stage_off + (unsigned)sizeof(P2) * (unsigned)(P < chunk_pairs ? gather_index(p, P) : 0);
                 }
                 desc_sm[q * kThreads] = make_uint4(d[0], d[1], d[2], d[3]);
             }
         } else {
             for (int P = threadIdx.x; P < p.lut_entries; P += blockDim.x) lut[P] = (uint16_t)gather_index(p, P);
         }
-        if (T.lane == 0) { stage[0] = mk_pair<OT>(p.DC, p.D); stage[1] = mk_pair<OT>(p.DL, p.DR); stage[2] = mk_pair<OT>(-1, -1); }
+        for (int e = T.lane; e < EPW; e += 32) {   // the constant pairs of every env template of this warp
+            P2 *t = stage + e * (2 * A + 4);
+            t[0] = mk_pair<OT>(0, 0); t[1] = mk_pair<OT>(p.DC, p.D); t[2] = mk_pair<OT>(p.DL, p.DR); t[2 * A + 3] = mk_pair<OT>(-1, -1);
+        }
     }
     for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
     for (int i = threadIdx.x; i < 2 * PH; i += blockDim.x) yt[(i / PH) * kMaxPad + i % PH] = make_yt(p, i / PH, i % PH - 1);
@@ -371,30 +378,59 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
     const int group_stride = EPW * A;
 
     const int total_warps = (int)gridDim.x * kWarpsPerCta;
-    for (int g = (int)blockIdx.x * kWarpsPerCta + warp; g < (int)p.n_groups; g += total_warps) {
+    const int n_groups = (int)p.n_groups;
+    // The record of group g + total_warps is fetched while group g is processed (software prefetch:
+    // the loads at the top of an iteration were the largest single stall of the kernel).
+    struct Record { unsigned x[APL], y[APL], fl[APL]; int act[APL]; int step; float ep_ret; };
+    auto fetch = [&](int gg, Record &r) {
+        const long long m0 = (long long)gg * EPW;
+        const bool ok = T.tile < (int)min((long long)EPW, p.n_envs - m0);   // false only in the ragged last group
+        const int tl = ok ? T.tile : 0;                                       // tiles beyond the end re-read env 0 of the group
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+            const int o = gg * group_stride + (ok ? aload[k] : aload[k] - T.tile * A);
+            r.x[k] = (unsigned)(uint8_t)p.x[o];
+            r.y[k] = (unsigned)(uint8_t)p.y[o];
+            r.fl[k] = p.flags[o];
+            r.act[k] = CC_ACT_WAIT;
+            if (kMoves && p.policy == CC_POLICY_EXTERNAL) r.act[k] = p.actions[o];
+        }
+        r.step = p.step[(int)m0 + tl];
+        r.ep_ret = kMoves ? p.ep_ret[(int)m0 + tl] : 0.f;
+    };
+    Record next;
+    int g = (int)blockIdx.x * kWarpsPerCta + warp;
+#if CCB_PREFETCH
+    if (g < n_groups) fetch(g, next);
+#endif
+    for (; g < n_groups; g += total_warps) {
+#if !CCB_PREFETCH
+        fetch(g, next);
+#endif
         const long long n0 = (long long)g * EPW;
         const int envs_here = (int)min((long long)EPW, p.n_envs - n0);
         const bool env_ok = T.tile < envs_here;           // false only in the ragged last group
         const int row0 = g * group_stride;                // first agent slot of the group (N*A < 2^31, checked by the host)
-        const int tload = env_ok ? T.tile : 0;            // tiles beyond the end re-read env 0 of the group
         const unsigned long long genv = p.genv_offset + (unsigned long long)(n0 + T.tile);
         int off[APL];
 #pragma unroll
         for (int k = 0; k < APL; ++k) off[k] = row0 + (env_ok ? aload[k] : aload[k] - T.tile * A);
 
-        // ---- load the env's record: branch-free, one contiguous run of bytes per array per warp ----
+        // ---- the env's record (one contiguous run of bytes per array per warp), prefetched ----------
         unsigned pos[APL];   // x << 8 | y (both 0..126 for every reachable state)
         unsigned fl[APL];
         int action[APL];
 #pragma unroll
         for (int k = 0; k < APL; ++k) {
-            pos[k] = ((unsigned)(uint8_t)p.x[off[k]] << 8) | (unsigned)(uint8_t)p.y[off[k]];
-            fl[k] = (env_ok && avalid[k]) ? (unsigned)p.flags[off[k]] : 0u;
-            action[k] = CC_ACT_WAIT;
-            if (kMoves && p.policy == CC_POLICY_EXTERNAL) action[k] = p.actions[off[k]];
+            pos[k] = (next.x[k] << 8) | next.y[k];
+            fl[k] = (env_ok && avalid[k]) ? next.fl[k] : 0u;
+            action[k] = next.act[k];
         }
-        int step = p.step[(int)n0 + tload];
-        float ep_ret = kMoves ? p.ep_ret[(int)n0 + tload] : 0.f;
+        int step = next.step;
+        float ep_ret = next.ep_ret;
+#if CCB_PREFETCH
+        if (g + total_warps < n_groups) fetch(g + total_warps, next);
+#endif
 
         // table coordinates (clamped: set_state promises in-lattice positions; the clamp only keeps
         // shared-memory reads in bounds for garbage) and the padded-lattice cell of every owned agent
@@ -746,7 +782,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
 
         // ---- observations.py:43-94 from the post-step (post-reset) state ------------------------
         if (kHasObs && p.obs != nullptr) {
-            P2 *tstage = stage + 3 + T.tile * 2 * A;
+            P2 *tstage = stage + T.tile * (2 * A + 4) + 3;
 #pragma unroll
             for (int k = 0; k < APL; ++k)
                 if (avalid[k]) {
@@ -756,43 +792,52 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             __syncwarp();
             OT *obs = reinterpret_cast<OT *>(p.obs);
             const long long gp0 = n0 * (long long)p.pairs_per_env;
+            P2 *out = reinterpret_cast<P2 *>(obs) + gp0;
+            const int count = envs_here * p.pairs_per_env;        // output pairs of this group
             if (MODE == kModeReset) {
                 // only the envs that were reset get their rows rewritten
                 const unsigned tiles = __ballot_sync(kFull, need_reset);
-                P2 *out = reinterpret_cast<P2 *>(obs) + gp0;
-                for (int P = T.lane; P < envs_here * p.pairs_per_env; P += 32)
+                for (int P = T.lane; P < count; P += 32)
                     if ((tiles >> ((P / p.pairs_per_env) * LPE)) & 1u) out[P] = stage[gather_index(p, P)];
-            } else if (kCanCache && cached && envs_here == EPW) {
-                // whole, vector-aligned chunk: each lane gathers its vectors through its descriptors
-                uint4 *outv = reinterpret_cast<uint4 *>(reinterpret_cast<P2 *>(obs) + gp0) + T.lane;
-                const int nvec = chunk_pairs / PPV, nfull = nvec >> 5;   // rows of 32 vectors all lanes store
+            } else if (kCanCache && cached && (kPairwise || envs_here == EPW)) {
                 uint4 d4 = make_uint4(0, 0, 0, 0);
+                if (kPairwise) {
+                    // lane <-> output pair: 32 lanes store 256 contiguous bytes per instruction
+                    P2 *o = out + T.lane;
 #pragma unroll
-                for (int j = 0; j < kDescWords / PPV; ++j) {
-                    if (j * 32 < nvec) {                                  // uniform
-                        union { uint4 u; P2 e[PPV]; } pk;
-#pragma unroll
-                        for (int h = 0; h < PPV; ++h) {
-                            const int w = j * PPV + h;
+                    for (int w = 0; w < kDescWords; ++w) {
+                        if (w * 32 < count) {                             // uniform
                             if (w % 4 == 0) d4 = desc_sm[(w / 4) * kThreads];
                             const unsigned a = (w % 4 == 0) ? d4.x : (w % 4 == 1) ? d4.y : (w % 4 == 2) ? d4.z : d4.w;
-                            P2 v;
-                            if (sizeof(P2) == 8) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(reinterpret_cast<float2 &>(v).x), "=f"(reinterpret_cast<float2 &>(v).y) : "r"(a));
-                            else { unsigned short hw; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hw) : "r"(a)); v = reinterpret_cast<P2 &>(hw); }
-                            pk.e[h] = v;
+                            const P2 v = *reinterpret_cast<const P2 *>(smem + a);
+                            if (w * 32 + 32 <= count || T.lane + w * 32 < count) __stcs(reinterpret_cast<float2 *>(o + 32 * w), reinterpret_cast<const float2 &>(v));
                         }
-                        if (j < nfull || T.lane < (nvec & 31)) __stcs(outv + 32 * j, pk.u);
+                    }
+                } else {
+                    // whole, vector-aligned chunk: each lane assembles its 16-byte vectors
+                    uint4 *outv = reinterpret_cast<uint4 *>(out) + T.lane;
+                    const int nvec = chunk_pairs / PPV;
+#pragma unroll
+                    for (int j = 0; j < kDescWords / PPV; ++j) {
+                        if (j * 32 < nvec) {                              // uniform
+                            union { uint4 u; P2 e[PPV]; } pk;
+#pragma unroll
+                            for (int h = 0; h < PPV; ++h) {
+                                const int w = j * PPV + h;
+                                if (w % 4 == 0) d4 = desc_sm[(w / 4) * kThreads];
+                                const unsigned a = (w % 4 == 0) ? d4.x : (w % 4 == 1) ? d4.y : (w % 4 == 2) ? d4.z : d4.w;
+                                pk.e[h] = *reinterpret_cast<const P2 *>(smem + a);
+                            }
+                            if (j * 32 + 32 <= nvec || T.lane + j * 32 < nvec) __stcs(outv + 32 * j, pk.u);
+                        }
                     }
                 }
+            } else if (cached) {
+                // ragged last group of an int8 run that otherwise uses the descriptors: the LUT was not
+                // built, gather with the index function directly (at most once per launch)
+                for (int P = T.lane; P < count; P += 32) out[P] = stage[gather_index(p, P)];
             } else {
-                if (cached) {
-                    // ragged last group of a run that otherwise uses the descriptors: the LUT was
-                    // not built, gather with the index function directly (once per launch at most)
-                    P2 *out = reinterpret_cast<P2 *>(obs) + gp0;
-                    for (int P = T.lane; P < envs_here * p.pairs_per_env; P += 32) out[P] = stage[gather_index(p, P)];
-                } else {
-                    emit_obs_lut<OT>(obs, gp0, envs_here * p.pairs_per_env, lut, stage, T.lane);
-                }
+                emit_obs_lut<OT>(obs, gp0, count, lut, stage, T.lane);
             }
             __syncwarp();
         }
