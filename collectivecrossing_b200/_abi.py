@@ -21,6 +21,7 @@ F_ACTIVE, F_TERMINATED, F_TRUNCATED = 1, 2, 4
 O_ACTIVE, O_TERMINATED, O_TRUNCATED, O_ALIVE_PREV, O_TERM_VALUE, O_TRUNC_VALUE, O_OBS_PRESENT = 1, 2, 4, 8, 16, 32, 64
 I_IN_TRAM_AREA, I_AT_DOOR, I_ACTIVE, I_AT_DESTINATION = 1, 2, 4, 8
 E_TERMINATED_ALL, E_TRUNCATED_ALL, E_WAS_RESET = 1, 2, 4
+KERNEL_VARIANTS = {"auto": 0, "lanes": 1, "threads": 2}
 
 
 class CCConfig(C.Structure):
@@ -88,6 +89,8 @@ EXPORTS = {
     "cc_step_counter": (_U64, [_P]),
     "cc_set_step_counter": (C.c_int, [_P, _U64]),
     "cc_launch_count": (_I64, [_P]),
+    "cc_set_kernel_variant": (C.c_int, [_P, _I32]),
+    "cc_last_kernel_variant": (_I32, [_P]),
     "cc_timing_begin": (C.c_int, [_P, _P]),
     "cc_timing_end": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
     "cc_last_error": (C.c_char_p, []),

@@ -88,7 +88,7 @@ class BatchedCollectiveCrossing:
 
     def __init__(self, config: Any, num_envs: int, device: Any = "cuda:0", *, seed: int = 0,
                  global_env_offset: int = 0, obs_dtype: str = "float32", reward_dtype: str = "float32",
-                 auto_reset: bool = True, with_info: bool = False):
+                 auto_reset: bool = True, with_info: bool = False, kernel: str = "auto"):
         self._lib = _native.library()  # raises ImportError when the CUDA library is not built
         if not torch.cuda.is_available():
             raise RuntimeError("collectivecrossing_b200 needs a CUDA device (no CPU fallback exists)")
@@ -130,6 +130,20 @@ class BatchedCollectiveCrossing:
         _native.check(self._lib.cc_attach_state(self._h, self.x.data_ptr(), self.y.data_ptr(), self.flags.data_ptr(),
                                                 self.step_count.data_ptr(), self.episode_return.data_ptr()))
         self._io = _abi.CCStepIO()
+        self.set_kernel(kernel)
+
+    def set_kernel(self, kernel: str) -> None:
+        """Work mapping of ``step``: "auto" (default), "lanes" (one lane per agent) or "threads" (one
+        thread per env; crews of 4 or 8).  Both mappings return identical results."""
+        if kernel not in _abi.KERNEL_VARIANTS:
+            raise ValueError(f"kernel must be one of {list(_abi.KERNEL_VARIANTS)}")
+        _native.check(self._lib.cc_set_kernel_variant(self._h, _abi.KERNEL_VARIANTS[kernel]))
+
+    @property
+    def last_kernel(self) -> str:
+        """Mapping the last ``step`` launch used ("none" before the first)."""
+        code = int(self._lib.cc_last_kernel_variant(self._h))
+        return {0: "none", 1: "lanes", 2: "threads"}[code]
 
     # ------------------------------------------------------------------------------------------
     def close(self) -> None:

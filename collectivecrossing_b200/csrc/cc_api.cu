@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 
+#include "cc_kernel_tpe.cuh"
 #include "cc_kernels.cuh"
 
 namespace {
@@ -54,6 +55,8 @@ struct cc_handle {
     ccb::Pcg64State *gen = nullptr;  // per-env numpy-compatible generators (allocated on first seeded reset)
     bool gen_seeded = false;
     int64_t launches = 0;
+    int variant = CC_KERNEL_AUTO;   // cc_set_kernel_variant
+    int last_variant = 0;           // mapping of the last step launch (CC_KERNEL_LANES / CC_KERNEL_THREADS)
     // host-path staging
     void *stage_block = nullptr;
     size_t stage_bytes = 0;
@@ -146,6 +149,52 @@ int launch(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s) {
     return fail(CC_ERR_UNSUPPORTED, "no kernel for %d agents", h->A);
 }
 
+// ---- thread-per-env step kernel (cc_kernel_tpe.cuh): crews of 4 or 8, agent order, float32 rewards ----
+template <int A, int OBS>
+int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
+    using L = ccb::TpeLayout<A, OBS>;
+    auto kern = ccb::cc_step_tpe_kernel<A, OBS>;
+    p.n_groups = (h->n_envs + 31) / 32;
+    const int smem = L::kStageBytes;
+    CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ccb::kTpeThreads, smem));
+    if (per_sm < 1) return fail(CC_ERR_UNSUPPORTED, "thread-per-env kernel does not fit on an SM (smem %d)", smem);
+    long long want = (p.n_groups + ccb::kTpeWarps - 1) / ccb::kTpeWarps;
+    long long cap = (long long)h->sm_count * per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, ccb::kTpeThreads, smem, s>>>(p);
+    CC_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return CC_OK;
+}
+
+bool aligned_to(const void *q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; }
+
+// which step launches the thread-per-env kernel can serve
+bool tpe_eligible(const cc_handle *h, const cc_step_io *io) {
+    const int A = h->A;
+    if (A != 8 && A != 4) return false;
+    if (io->order || io->reward_dtype != CC_REWARD_F32) return false;      // dict order / float64 rewards: lane-group kernel
+    if (io->obs_dtype == CC_OBS_INT8 && A != 8) return false;              // an env's int8 block must be whole 16-byte vectors
+    const void *rows[] = {h->x, h->y, h->flags, io->actions, io->actions_out, io->agent_flags, io->agent_info};
+    for (const void *q : rows)
+        if (q && !aligned_to(q, (uintptr_t)A)) return false;
+    return aligned_to(io->reward, 16) && aligned_to(h->step, 4) && aligned_to(h->ep_ret, 4);
+}
+
+int launch_tpe(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s) {
+    switch (h->A * 8 + obs_dtype) {
+    case 8 * 8 + CC_OBS_NONE: return launch_tpe_t<8, CC_OBS_NONE>(h, p, s);
+    case 8 * 8 + CC_OBS_INT8: return launch_tpe_t<8, CC_OBS_INT8>(h, p, s);
+    case 8 * 8 + CC_OBS_FP32: return launch_tpe_t<8, CC_OBS_FP32>(h, p, s);
+    case 4 * 8 + CC_OBS_NONE: return launch_tpe_t<4, CC_OBS_NONE>(h, p, s);
+    case 4 * 8 + CC_OBS_FP32: return launch_tpe_t<4, CC_OBS_FP32>(h, p, s);
+    }
+    return fail(CC_ERR_UNSUPPORTED, "no thread-per-env kernel for %d agents, obs_dtype %d", h->A, obs_dtype);
+}
+
 int check_io(const cc_handle *h, const cc_step_io *io) {
     if (!h || !io) return fail(CC_ERR_INVALID_ARG, "null handle or io");
     if (io->policy < CC_POLICY_EXTERNAL || io->policy > CC_POLICY_WAITING) return fail(CC_ERR_INVALID_ARG, "unknown policy %d", io->policy);
@@ -165,8 +214,13 @@ int step_on(cc_handle *h, const cc_step_io *io, cudaStream_t s) {
     p.actions = io->actions; p.order = io->order; p.actions_out = io->actions_out;
     p.obs = io->obs; p.reward = io->reward; p.agent_flags = io->agent_flags; p.agent_info = io->agent_info; p.env_flags = io->env_flags;
     p.policy = io->policy; p.auto_reset = io->auto_reset != 0; p.reward_f64 = io->reward_dtype == CC_REWARD_F64;
-    int rc = launch<ccb::kModeStep>(h, p, io->obs_dtype, s);
-    if (rc == CC_OK) h->t += 1;
+    const bool can_tpe = tpe_eligible(h, io);
+    if (h->variant == CC_KERNEL_THREADS && !can_tpe)
+        return fail(CC_ERR_UNSUPPORTED, "CC_KERNEL_THREADS was requested but this step is not eligible (needs 4 or 8 agents, agent order, "
+                                        "float32 rewards, rows aligned to the crew size)");
+    const bool use_tpe = can_tpe && h->variant != CC_KERNEL_LANES;
+    int rc = use_tpe ? launch_tpe(h, p, io->obs_dtype, s) : launch<ccb::kModeStep>(h, p, io->obs_dtype, s);
+    if (rc == CC_OK) { h->t += 1; h->last_variant = use_tpe ? CC_KERNEL_THREADS : CC_KERNEL_LANES; }
     return rc;
 }
 
@@ -425,6 +479,13 @@ int32_t cc_obs_len(const cc_handle *h) { return h ? 6 + 4 * h->A : 0; }
 uint64_t cc_step_counter(const cc_handle *h) { return h ? h->t : 0; }
 int cc_set_step_counter(cc_handle *h, uint64_t t) { if (!h) return fail(CC_ERR_INVALID_ARG, "null handle"); h->t = t; return CC_OK; }
 int64_t cc_launch_count(const cc_handle *h) { return h ? h->launches : 0; }
+int cc_set_kernel_variant(cc_handle *h, int32_t variant) {
+    if (!h) return fail(CC_ERR_INVALID_ARG, "null handle");
+    if (variant != CC_KERNEL_AUTO && variant != CC_KERNEL_LANES && variant != CC_KERNEL_THREADS) return fail(CC_ERR_INVALID_ARG, "unknown kernel variant %d", variant);
+    h->variant = variant;
+    return CC_OK;
+}
+int32_t cc_last_kernel_variant(const cc_handle *h) { return h ? h->last_variant : 0; }
 
 int cc_timing_begin(cc_handle *h, void *stream) {
     if (!h) return fail(CC_ERR_INVALID_ARG, "null handle");

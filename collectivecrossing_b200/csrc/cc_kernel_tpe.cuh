@@ -1,0 +1,468 @@
+// cc_kernel_tpe.cuh — the step kernel for small crews (A <= 8): one THREAD owns one env.
+//
+// Why a second mapping: with one lane per agent (cc_kernels.cuh) a README env costs
+// ~160 warp-instructions per step and the kernel is bound by the issue rate, not by HBM.  For A <= 8
+// the whole env fits in the registers of one thread, the reference's sequential move loop
+// (collectivecrossing.py:197-202) becomes straight-line code, and a warp steps 32 envs with the
+// instruction count the lane-group mapping needs for 4.  What is left is the byte traffic:
+//   * state / actions / per-agent outputs: an env's A bytes are ONE 8-byte (A = 8) or 4-byte (A = 4)
+//     word per thread — consecutive threads, consecutive words: coalesced without staging;
+//   * observations: every thread writes its env's row template into shared memory (conflict-free
+//     16-byte stores), then the warp streams the 32 envs' rows (38.9 KB for A = 8, float32) to HBM as
+//     consecutive 16-byte vectors, each assembled from two template pairs through a per-CTA table
+//     of template offsets (the map is periodic in the env).
+// Semantics, quirks and RNG streams are those of cc_kernels.cuh / oracle/cc_oracle.c; every block
+// cites the reference lines it restates (paths relative to /root/reference/src/collectivecrossing/).
+#pragma once
+#include "cc_kernels.cuh"
+
+#ifndef CCB_TPE_MIN_BLOCKS
+#define CCB_TPE_MIN_BLOCKS 3   // resident CTAs per SM the register allocator must allow
+#endif
+
+namespace ccb {
+
+constexpr int kTpeWarps = 8;
+constexpr int kTpeThreads = kTpeWarps * 32;
+
+template <int A, int OBS>
+struct TpeLayout {
+    using OT = typename std::conditional<OBS == CC_OBS_FP32, float, int8_t>::type;
+    using P2 = typename PairOf<OT>::type;
+    static constexpr bool kHasObs = OBS != CC_OBS_NONE;
+    static constexpr int R = 3 + 2 * A;                  // pairs per observation row
+    static constexpr int PPE = A * R;                    // pairs per env
+    static constexpr int PSZ = (int)sizeof(P2);          // 8 (float32) or 2 (int8)
+    static constexpr int PPV = 16 / PSZ;                 // pairs per 16-byte vector
+    static constexpr bool kVectorisable = PPE % PPV == 0;
+    static constexpr int VPE = PPE / PPV;                // 16-byte vectors per env
+    // row template of one env: [S_0a, S_0b, ..., S_(A-1)a, S_(A-1)b, K1, K2, M]  (2A+3 pairs); its
+    // stride is an ODD number of store units (16 B for float32, 4 B for int8) so that the 32 threads
+    // of a warp write their templates without bank conflicts
+    static constexpr int TPL_PAIRS = 2 * A + 3;
+    static constexpr int UNIT = OBS == CC_OBS_FP32 ? 16 : 4;
+    static constexpr int TSB = (((TPL_PAIRS * PSZ + UNIT - 1) / UNIT) | 1) * UNIT;
+    static constexpr int kStageBytesPerWarp = kHasObs ? 32 * TSB : 0;
+    static constexpr int kStageBytes = kTpeWarps * kStageBytesPerWarp;
+    static constexpr int kLutWords = kHasObs ? VPE * PPV / 2 : 1;   // two 16-bit template offsets per word
+};
+
+// byte offset, inside an env's row template, of the pair that feeds output pair q of row i
+// (observations.py:62-94: own position, door constants, then every agent's block with the own block masked)
+template <int A, int PSZ>
+__device__ __forceinline__ unsigned tpe_template_offset(int i, int q) {
+    int idx;
+    if (q == 0) idx = 2 * i;
+    else if (q == 1) idx = 2 * A;
+    else if (q == 2) idx = 2 * A + 1;
+    else idx = ((q - 3) >> 1) == i ? 2 * A + 2 : q - 3;
+    return (unsigned)(idx * PSZ);
+}
+
+// A bytes of env `env` of an [N][A] byte array as one word per thread where A allows it
+template <int A>
+__device__ __forceinline__ void tpe_load_row(const void *base, int env, unsigned (&v)[A]) {
+    const unsigned char *q = static_cast<const unsigned char *>(base) + (size_t)env * A;
+    if constexpr (A == 8) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k] = (w.x >> (8 * k)) & 0xffu; v[4 + k] = (w.y >> (8 * k)) & 0xffu; }
+    } else if constexpr (A == 4) {
+        const unsigned w = *reinterpret_cast<const unsigned *>(q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (w >> (8 * k)) & 0xffu;
+    } else {
+#pragma unroll
+        for (int k = 0; k < A; ++k) v[k] = q[k];
+    }
+}
+template <int A>
+__device__ __forceinline__ void tpe_store_row(void *base, int env, const unsigned (&v)[A]) {
+    unsigned char *q = static_cast<unsigned char *>(base) + (size_t)env * A;
+    if constexpr (A == 8) {
+        uint2 w;
+        w.x = (v[0] & 0xffu) | ((v[1] & 0xffu) << 8) | ((v[2] & 0xffu) << 16) | (v[3] << 24);
+        w.y = (v[4] & 0xffu) | ((v[5] & 0xffu) << 8) | ((v[6] & 0xffu) << 16) | (v[7] << 24);
+        *reinterpret_cast<uint2 *>(q) = w;
+    } else if constexpr (A == 4) {
+        *reinterpret_cast<unsigned *>(q) = (v[0] & 0xffu) | ((v[1] & 0xffu) << 8) | ((v[2] & 0xffu) << 16) | (v[3] << 24);
+    } else {
+#pragma unroll
+        for (int k = 0; k < A; ++k) q[k] = (unsigned char)v[k];
+    }
+}
+
+template <int A, int OBS>
+__global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_kernel(const __grid_constant__ KParams p) {
+    using L = TpeLayout<A, OBS>;
+    using OT = typename L::OT;
+    using P2 = typename L::P2;
+    constexpr bool kHasObs = L::kHasObs;
+    constexpr unsigned kGhost = 0xFFFFFFFFu;
+    static_assert(A >= 1 && A <= 8, "thread-per-env mapping is for crews of at most 8");
+    static_assert(!kHasObs || L::kVectorisable, "an env's observation block must be a whole number of 16-byte vectors");
+    extern __shared__ __align__(16) unsigned char smem[];   // row templates: [warp][32 envs][TSB]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int PW = p.W + 3, PH = p.H + 3;  // lattice padded by one ring: x in [-1, W+1] -> column x+1
+    __shared__ unsigned xt[kMaxPad], yt[2 * kMaxPad], walk[kMaxWalkWords];
+    __shared__ float rtab[2 * kRtabSize];
+    __shared__ uint8_t act_tab[kPolicyRows * 16];
+    __shared__ unsigned long long red_all[kTpeWarps * kStCount];
+    __shared__ __align__(16) unsigned lut[L::kLutWords];
+    unsigned char *wstage = smem + warp * L::kStageBytesPerWarp;   // this warp's 32 templates
+    unsigned char *tpl = wstage + lane * L::TSB;                    // this thread's env
+
+    // ---- once per CTA: tables (same contents as cc_kernels.cuh) -------------------------------------
+    for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
+    for (int i = threadIdx.x; i < 2 * PH; i += blockDim.x) yt[(i / PH) * kMaxPad + i % PH] = make_yt(p, i / PH, i % PH - 1);
+    for (int i = threadIdx.x; i < kPolicyRows * 16; i += blockDim.x) act_tab[i] = (uint8_t)greedy_decision(i >> 4, (unsigned)i & 15u);
+    {
+        // distance rewards: float((double)(-+d) * f), the reference's float64 product rounded once
+        // (rewards.py:85,99,127); constants for binary / constant_negative (rewards.py:152-159,179-182)
+        const double f = p.reward_kind == CC_REWARD_DEFAULT ? p.rp[3] : p.rp[0];
+        for (int i = threadIdx.x; i < 2 * kRtabSize; i += blockDim.x) {
+            const int type = i / kRtabSize, d = i % kRtabSize - kYBias;
+            const bool negate = type == 0 || p.reward_kind == CC_REWARD_SIMPLE_DISTANCE;
+            float v = (float)((double)(negate ? -d : d) * f);
+            if (p.reward_kind == CC_REWARD_BINARY) v = p.rpf[1];
+            if (p.reward_kind == CC_REWARD_CONSTANT_NEGATIVE) v = p.rpf[0];
+            rtab[i] = v;
+        }
+    }
+    for (int w = threadIdx.x; w < p.walk_words; w += blockDim.x) {   // collectivecrossing.py:509-534 as a bitmap
+        unsigned bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int idx = w * 32 + b, yy = idx / PW - 1, xx = idx - (yy + 1) * PW - 1;
+            bits |= valid_position(p, xx, yy) ? (1u << b) : 0u;
+        }
+        walk[w] = bits;
+    }
+    if (kHasObs) {
+        for (int w = threadIdx.x; w < L::kLutWords; w += blockDim.x) {
+            const int P0 = 2 * w, P1 = 2 * w + 1;   // consecutive output pairs of an env
+            lut[w] = tpe_template_offset<A, L::PSZ>(P0 / L::R, P0 % L::R) | (tpe_template_offset<A, L::PSZ>(P1 / L::R, P1 % L::R) << 16);
+        }
+        // the constant pairs of this thread's template
+        P2 *t = reinterpret_cast<P2 *>(tpl);
+        t[2 * A] = mk_pair<OT>(p.DC, p.D); t[2 * A + 1] = mk_pair<OT>(p.DL, p.DR); t[2 * A + 2] = mk_pair<OT>(-1, -1);
+    }
+    unsigned long long *red = red_all + warp * kStCount;
+    if (lane < kStCount) red[lane] = 0ull;
+    __syncthreads();
+    unsigned st_arrivals = 0;
+    double st_rsum = 0.0;
+    int errbits = 0;
+
+    const int total_warps = (int)gridDim.x * kTpeWarps;
+    const int n_groups = (int)p.n_groups;   // groups of 32 envs
+    for (int g = (int)blockIdx.x * kTpeWarps + warp; g < n_groups; g += total_warps) {
+        const int n = g * 32 + lane;
+        const int envs_here = (int)min(32ll, p.n_envs - (long long)g * 32);
+        const bool env_ok = lane < envs_here;                 // false only in the ragged last group
+        const int nl = env_ok ? n : (int)p.n_envs - 1;        // threads beyond the end re-read the last env (never stored)
+        const unsigned long long genv = p.genv_offset + (unsigned long long)n;
+
+        // ---- the env's record -------------------------------------------------------------------
+        unsigned px[A], py[A], fl[A], action[A];
+        tpe_load_row<A>(p.x, nl, px);
+        tpe_load_row<A>(p.y, nl, py);
+        tpe_load_row<A>(p.flags, nl, fl);
+        if (p.policy == CC_POLICY_EXTERNAL) tpe_load_row<A>(p.actions, nl, action);
+        else {
+#pragma unroll
+            for (int k = 0; k < A; ++k) action[k] = CC_ACT_WAIT;
+        }
+        int step = p.step[nl];
+        float ep_ret = p.ep_ret[nl];
+        unsigned pos[A];
+#pragma unroll
+        for (int k = 0; k < A; ++k) { pos[k] = (px[k] << 8) | py[k]; fl[k] = env_ok ? fl[k] : 0u; }
+
+        int cell[A];
+        unsigned geo_u[A], geo_f[A];
+        auto lookup = [&](int k) {
+            const int cx = min((int)(pos[k] >> 8), p.W + 1) + 1, cy = min((int)(pos[k] & 0xffu), p.H + 1) + 1;
+            const unsigned xv = xt[cx], yv = yt[(k < p.B ? 0 : kMaxPad) + cy];
+            cell[k] = cy * PW + cx;
+            geo_u[k] = yv + xv;
+            geo_f[k] = (yv & xv) >> 24;
+        };
+        auto walkable = [&](int c) { return (walk[(c >> 5) & (kMaxWalkWords - 1)] >> (c & 31)) & 1u; };
+        // cmp[k] = packed position of an ACTIVE agent, else a sentinel no target can equal: inactive
+        // agents are ghosts (collectivecrossing.py:536-541)
+        unsigned cmp[A];
+#pragma unroll
+        for (int k = 0; k < A; ++k) cmp[k] = (fl[k] & CC_F_ACTIVE) ? pos[k] : kGhost;
+        auto occupied = [&](unsigned target) {
+            bool hit = false;
+#pragma unroll
+            for (int j = 0; j < A; ++j) hit |= cmp[j] == target;
+            return hit;
+        };
+
+        // ---- on-device policies (baseline_policies/*.py at randomness_factor 0) --------------------
+        bool geo_known = false;   // chosen moves already passed the geometric test
+        if (p.policy == CC_POLICY_RANDOM) {
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                action[k] = (unsigned)bounded(draw(p, genv, kStreamAction, (unsigned)k).v0, 5);
+                lookup(k);
+            }
+        } else if (p.policy != CC_POLICY_EXTERNAL) {
+            bool pending = false;
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                lookup(k);
+                // waiting_policy.py:118-131: some exiting agent that is not done has not arrived
+                pending |= k >= p.B && (fl[k] & 6u) == 0u && env_ok && !(geo_f[k] & 8u);
+            }
+            const bool exiting_pending = p.policy == CC_POLICY_WAITING && pending;
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                // validity of the four moves (greedy_policy.py:238-264 -> _is_move_valid, :345-369):
+                // walkable target that no ACTIVE agent holds (the asking agent's own cell is never a target)
+                const int c = cell[k];
+                const unsigned q = pos[k];
+                const unsigned v0 = walkable(c + 1) & (unsigned)!occupied((q + 0x100u) & 0xffffu);
+                const unsigned v1 = walkable(c + PW) & (unsigned)!occupied((q + 1u) & 0xffffu);
+                const unsigned v2 = walkable(c - 1) & (unsigned)!occupied((q - 0x100u) & 0xffffu);
+                const unsigned v3 = walkable(c - PW) & (unsigned)!occupied((q - 1u) & 0xffffu);
+                const unsigned vmask = v0 | (v1 << 1) | (v2 << 2) | (v3 << 3);
+                const unsigned a = act_tab[((geo_u[k] & 0xffu) << 4) | vmask];
+                const bool asks = (fl[k] & 7u) == CC_F_ACTIVE;                         // active, not done
+                const bool waits = exiting_pending && k < p.B && !(geo_f[k] & 1u);    // waiting_policy.py:74-108
+                action[k] = (asks && !waits) ? a : (unsigned)CC_ACT_WAIT;
+            }
+            geo_known = true;
+        } else {
+#pragma unroll
+            for (int k = 0; k < A; ++k) lookup(k);
+        }
+        if (p.actions_out && env_ok) tpe_store_row<A>(p.actions_out, n, action);
+
+        // ---- collectivecrossing.py:188 ---------------------------------------------------------------
+        step += 1;
+        unsigned alive_prev[A];   // 1 iff neither terminated nor truncated at step start
+#pragma unroll
+        for (int k = 0; k < A; ++k) alive_prev[k] = (env_ok && (fl[k] & 6u) == 0u) ? 1u : 0u;
+
+        // ---- collectivecrossing.py:197-202: moves, strictly in agent order ----------------------
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+            const unsigned a = action[k];
+            if (env_ok && a > 4u) errbits |= kErrInvalidAction;                          // :707-711
+            // packed (dx << 8 | dy) mod 2^16 of actions 0..3 (actions.py:18-24)
+            const unsigned delta = (unsigned)((0xFFFFFF0000010100ull >> (16 * (a & 3u))) & 0xffffull);
+            bool go = (fl[k] & CC_F_ACTIVE) && a < 4u;                                   // :398, wait
+            if (!geo_known) go = go && walkable(cell[k] + ((a & 1u) ? PW : 1) * ((a & 2u) ? -1 : 1));  // :509-534
+            const unsigned target = (pos[k] + delta) & 0xffffu;
+            if (go && !occupied(target)) cmp[k] = target;                                // :406-408
+        }
+#pragma unroll
+        for (int k = 0; k < A; ++k) pos[k] = (fl[k] & CC_F_ACTIVE) ? cmp[k] : pos[k];    // ghosts never move
+
+        // ---- :210-212 deactivate arrivals; rewards; terminated; truncated ----------------------
+        unsigned arr[A];
+        bool all_arrived = true;
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+            lookup(k);                                             // geometry of the post-move cell
+            arr[k] = (geo_f[k] >> 3) & 1u;                         // :663-683 (y only)
+            st_arrivals += (env_ok && arr[k] && (fl[k] & CC_F_ACTIVE)) ? 1u : 0u;
+            fl[k] &= ~arr[k];                                      // types.py:46-51 (CC_F_ACTIVE == 1)
+            all_arrived = all_arrived && arr[k];
+        }
+        const bool over_limit = step >= p.max_steps;               // truncateds.py:61
+        bool any_alive = false;
+        float rew[A];
+        unsigned oflag[A];
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+            // one path for the four reward functions, see cc_kernels.cuh (rewards.py:65-66,78-99,127,152-159,179-182)
+            const unsigned f = geo_f[k];
+            float r = rtab[(k < p.B ? 0 : kRtabSize) + (int)((geo_u[k] >> 8) & 0x1ffu)];
+            const bool boarding = k < p.B;
+            const float special = boarding ? ((f & 2u) ? p.rpf[1] : p.rpf[2]) : p.rpf[2];
+            const unsigned in_special = boarding ? (f & 3u) : ((f & 1u) ^ 1u);
+            r = (in_special & p.reward_category_mask) ? special : r;
+            r = (f & 8u & p.reward_category_mask) ? p.rpf[0] : r;
+            r = alive_prev[k] ? r : 0.f;
+            rew[k] = r;
+            any_alive |= alive_prev[k] != 0u;
+            const unsigned tval = (p.terminated_kind == CC_TERM_ALL_AT_DESTINATION) ? (unsigned)all_arrived : arr[k];  // terminateds.py:56-60,82
+            const unsigned cval = alive_prev[k] & (unsigned)over_limit;                   // truncateds.py:57-61
+            const unsigned present = alive_prev[k] | (tval & ~(fl[k] >> 1) & 1u);         // collectivecrossing.py:243
+            fl[k] |= (tval << 1) | (cval << 2);                                           // :229-241
+            oflag[k] = (fl[k] & 7u) | (alive_prev[k] << 3) | (tval << 4) | (cval << 5) | (present << 6);
+        }
+        const bool term_all = all_arrived;                          // :256
+        const bool trunc_all = any_alive && over_limit;             // :257
+        // reward sum of the env: the balanced float32 tree the lane-group kernel and the oracle use
+        // (leaves = lanes of a 4- or 8-lane tile, missing leaves 0)
+        float rsum;
+        {
+            constexpr int LPE = A <= 4 ? 4 : 8;
+            float leaf[LPE];
+#pragma unroll
+            for (int l = 0; l < LPE; ++l) leaf[l] = l < A ? 0.f + rew[l < A ? l : 0] : 0.f;
+#pragma unroll
+            for (int w = LPE / 2; w >= 1; w >>= 1)
+#pragma unroll
+                for (int l = 0; l < w; ++l) leaf[l] = leaf[l] + leaf[l + w];
+            rsum = leaf[0];
+        }
+        ep_ret += rsum;
+        const bool done = term_all || trunc_all;
+        unsigned eflags = (term_all ? CC_E_TERMINATED_ALL : 0u) | (trunc_all ? CC_E_TRUNCATED_ALL : 0u);
+
+        // ---- outputs of the finished step ----------------------------------------------------------
+        if (env_ok) {
+            float *rw = reinterpret_cast<float *>(p.reward) + (size_t)n * A;
+            if constexpr (A % 4 == 0) {
+#pragma unroll
+                for (int k = 0; k < A; k += 4) *reinterpret_cast<float4 *>(rw + k) = make_float4(rew[k], rew[k + 1], rew[k + 2], rew[k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < A; ++k) rw[k] = rew[k];
+            }
+            tpe_store_row<A>(p.agent_flags, n, oflag);
+            if (p.agent_info) {
+                unsigned info[A];
+#pragma unroll
+                for (int k = 0; k < A; ++k) info[k] = (geo_f[k] & 0xBu) | ((fl[k] & 1u) << 2);   // :248-254
+                tpe_store_row<A>(p.agent_info, n, info);
+            }
+            st_rsum += (double)rsum;
+        }
+        const bool ended = env_ok && done && any_alive;             // the step the last agents finished on
+        const unsigned ended_mask = __ballot_sync(kFull, ended);
+        if (ended_mask) {                                           // rare: fold this warp's finished episodes into its slot
+            const unsigned n_term = __popc(__ballot_sync(kFull, ended && term_all)), n_trunc = __popc(__ballot_sync(kFull, ended && trunc_all));
+            unsigned len = ended ? (unsigned)step : 0u;
+            double ret = ended ? (double)ep_ret : 0.0;
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) { len += __shfl_xor_sync(kFull, len, w); ret += __shfl_xor_sync(kFull, ret, w); }
+            if (lane == 0) {
+                red[kStEpisodes] += __popc(ended_mask); red[kStTermAll] += n_term; red[kStTruncAll] += n_trunc; red[kStEpLen] += len;
+                red[kStEpRet] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)red[kStEpRet]) + ret);
+            }
+        }
+
+        // ---- collectivecrossing.py:91-150 reset(): rejection-sampled placement (auto-reset) -------
+        // Agent i's k-th candidate is Philox(seed; genv, t, RESET, i<<16|k); it takes the first candidate
+        // that passes the geometric test and is not held by an agent j < i (cc_oracle.c:orc_reset_env).
+        if (env_ok && done && p.auto_reset) {
+            eflags |= CC_E_WAS_RESET;
+            ep_ret = 0.f;
+            step = 0;                                               // :97
+#pragma unroll
+            for (int i = 0; i < A; ++i) {
+                unsigned cand = 0;
+                bool ok = false;
+                for (int attempt = 0; attempt < kResetAttemptCap && !ok; ++attempt) {
+                    const U4 r = draw(p, genv, kStreamReset, ((unsigned)i << 16) | (unsigned)attempt);
+                    int cx, cy;
+                    if (i < p.B) {                                  // :103-117
+                        cx = bounded(r.v0, p.W); cy = bounded(r.v1, p.D);
+                        ok = valid_position(p, cx, cy) && !(p.DL <= cx && cx <= p.DR && cy == p.D - 1);
+                    } else {                                        // :132-140
+                        cx = p.TL + bounded(r.v0, p.TR + 1 - p.TL); cy = p.D + bounded(r.v1, p.H - p.D);
+                        ok = valid_position(p, cx, cy);
+                    }
+                    cand = pack_pos(cx, cy);
+#pragma unroll
+                    for (int j = 0; j < i; ++j) ok = ok && pos[j] != cand;
+                }
+                if (!ok) errbits |= kErrResetStuck;                 // cap hit: keep the last candidate
+                pos[i] = cand;
+                fl[i] = CC_F_ACTIVE;
+            }
+        }
+
+        // ---- write back the persistent state ----------------------------------------------------
+        if (env_ok) {
+#pragma unroll
+            for (int k = 0; k < A; ++k) { px[k] = pos[k] >> 8; py[k] = pos[k] & 0xffu; fl[k] &= 7u; }
+            tpe_store_row<A>(p.x, n, px);
+            tpe_store_row<A>(p.y, n, py);
+            tpe_store_row<A>(p.flags, n, fl);
+            p.step[n] = step;
+            p.ep_ret[n] = ep_ret;
+            p.env_flags[n] = (uint8_t)eflags;
+        }
+
+        // ---- observations.py:43-94 from the post-step (post-reset) state --------------------------
+        if (kHasObs) {
+            if constexpr (OBS == CC_OBS_FP32) {
+#pragma unroll
+                for (int k = 0; k < A; ++k)
+                    reinterpret_cast<float4 *>(tpl)[k] = make_float4((float)(int)(pos[k] >> 8), (float)(int)(pos[k] & 0xffu), k < p.B ? 0.f : 1.f, (float)(fl[k] & 1u));
+            } else {
+#pragma unroll
+                for (int k = 0; k < A; ++k)
+                    reinterpret_cast<unsigned *>(tpl)[k] = (pos[k] >> 8) | ((pos[k] & 0xffu) << 8) | ((k < p.B ? 0u : 1u) << 16) | ((fl[k] & 1u) << 24);
+            }
+            __syncwarp();
+            uint4 *outv = reinterpret_cast<uint4 *>(p.obs) + (size_t)g * 32 * L::VPE + lane;
+            const unsigned char *tb = wstage;   // template of the env the lane's current vector belongs to
+            int r = lane;                       // vector index inside that env
+            while (r >= L::VPE) { r -= L::VPE; tb += L::TSB; }
+            auto emit = [&](uint4 *dst) {
+                uint4 o;
+                if constexpr (OBS == CC_OBS_FP32) {
+                    const unsigned l = lut[r];
+                    const float2 a = *reinterpret_cast<const float2 *>(tb + (l & 0xffffu));
+                    const float2 b = *reinterpret_cast<const float2 *>(tb + (l >> 16));
+                    o = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(b.x), __float_as_uint(b.y));
+                } else {
+                    const uint4 l = reinterpret_cast<const uint4 *>(lut)[r];
+                    auto two = [&](unsigned w) {
+                        return (unsigned)*reinterpret_cast<const unsigned short *>(tb + (w & 0xffffu)) |
+                               ((unsigned)*reinterpret_cast<const unsigned short *>(tb + (w >> 16)) << 16);
+                    };
+                    o = make_uint4(two(l.x), two(l.y), two(l.z), two(l.w));
+                }
+                __stcs(dst, o);
+                r += 32;
+                while (r >= L::VPE) { r -= L::VPE; tb += L::TSB; }
+            };
+            if (envs_here == 32) {
+#pragma unroll 4
+                for (int j = 0; j < L::VPE; ++j) emit(outv + 32 * j);    // 32 envs x VPE vectors = VPE per lane
+            } else {
+                const int nvec = envs_here * L::VPE;
+                for (int v = lane; v < nvec; v += 32) emit(outv + (v - lane));
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- statistics: per-warp slots in shared memory -> one atomic per slot per CTA ----------------
+    {
+        double rs = st_rsum;
+        unsigned ar = st_arrivals;
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) { rs += __shfl_xor_sync(kFull, rs, w); ar += __shfl_xor_sync(kFull, ar, w); }
+        if (lane == 0) {
+            red[kStArrivals] += ar;
+            red[kStRewardSum] = (unsigned long long)__double_as_longlong(rs);
+        }
+        __syncthreads();
+        const unsigned long long *all = red_all;
+        if (threadIdx.x >= 1 && threadIdx.x < 6) {
+            unsigned long long v = 0;
+            for (int w = 0; w < kTpeWarps; ++w) v += all[w * kStCount + threadIdx.x];
+            if (v) atomicAdd(&p.stats[threadIdx.x], v);
+        } else if (threadIdx.x == 6 || threadIdx.x == 7) {
+            double v = 0.0;
+            for (int w = 0; w < kTpeWarps; ++w) v += __longlong_as_double((long long)all[w * kStCount + threadIdx.x]);
+            if (v != 0.0) atomicAdd(reinterpret_cast<double *>(&p.stats[threadIdx.x]), v);
+        } else if (threadIdx.x == 0 && blockIdx.x == 0) {
+            atomicAdd(&p.stats[kStEnvSteps], (unsigned long long)p.n_envs);
+        }
+    }
+    if (errbits) atomicOr(p.err, errbits);
+}
+
+}  // namespace ccb

@@ -227,6 +227,15 @@ uint64_t cc_step_counter(const cc_handle *h);        /* launches so far (RNG cou
 int cc_set_step_counter(cc_handle *h, uint64_t t);   /* for checkpoint / resume */
 /* number of kernels the library launched through this handle (bench "gpu_launches") */
 int64_t cc_launch_count(const cc_handle *h);
+/* Which work mapping cc_step uses.  Both produce identical results (tests/test_gpu_parity.py
+ * runs every case through both):
+ *   CC_KERNEL_LANES    one lane per agent, 4-32 lanes per env (any crew size, dict order, float64 rewards);
+ *   CC_KERNEL_THREADS  one thread per env (crews of 4 or 8, agent order, float32 rewards);
+ *   CC_KERNEL_AUTO     THREADS where eligible, else LANES (default).
+ * Requesting CC_KERNEL_THREADS makes ineligible steps fail with CC_ERR_UNSUPPORTED. */
+enum { CC_KERNEL_AUTO = 0, CC_KERNEL_LANES = 1, CC_KERNEL_THREADS = 2 };
+int cc_set_kernel_variant(cc_handle *h, int32_t variant);
+int32_t cc_last_kernel_variant(const cc_handle *h); /* mapping of the last cc_step launch (0 = none yet) */
 /* average device time (ms) of the step kernel launches bracketed by cc_timing_begin/_end,
  * measured with CUDA events on the launching stream */
 int cc_timing_begin(cc_handle *h, void *stream);

@@ -39,13 +39,13 @@ def replay_oracle(cfg, rec, policy="external", use_order=True):
     return got
 
 
-def replay_device(cfg, rec, policy="external", use_order=True, obs_dtype="int8", reward_dtype="float64", device="cuda:0"):
+def replay_device(cfg, rec, policy="external", use_order=True, obs_dtype="int8", reward_dtype="float64", device="cuda:0", kernel="auto"):
     import torch
 
     from collectivecrossing_b200 import BatchedCollectiveCrossing
 
     T, N, A = rec["actions"].shape
-    env = BatchedCollectiveCrossing(cfg, N, device, obs_dtype=obs_dtype, reward_dtype=reward_dtype, auto_reset=False, with_info=True)
+    env = BatchedCollectiveCrossing(cfg, N, device, obs_dtype=obs_dtype, reward_dtype=reward_dtype, auto_reset=False, with_info=True, kernel=kernel)
     dev = env.device
     env.set_state(torch.from_numpy(rec["init_x"]).to(dev), torch.from_numpy(rec["init_y"]).to(dev),
                   torch.from_numpy(rec["init_flags"]).to(dev), torch.from_numpy(rec["init_step"]).to(dev))
@@ -64,6 +64,7 @@ def replay_device(cfg, rec, policy="external", use_order=True, obs_dtype="int8",
         got["obs"][t] = out.obs.cpu().numpy().astype(np.int8)
         got["actions"][t] = out.actions.cpu().numpy()
     env.check_error()
+    got["_kernel"] = env.last_kernel
     env.close()
     return got
 

@@ -52,10 +52,29 @@ def test_device_fp32_outputs_match_golden_within_tolerance():
     assert_same(rec, got, "device-fp32", reward_rtol=1e-6)
 
 
+# ---- the thread-per-env mapping against the REFERENCE's recordings -------------------------------
+@pytest.mark.parametrize("name", ["readme_greedy", "readme_waiting", "readme_binary_all", "readme_simple_all", "readme_constneg_ind"])
+def test_thread_per_env_kernel_replays_golden(name):
+    """float32 rewards + agent order make a README step eligible for the thread-per-env kernel:
+    positions, flags, observations, infos and policy actions bit-exact with the reference's
+    recording, rewards within the north_star tolerance (1e-6 relative; they are in fact the
+    correctly rounded float32 of the reference's float64)."""
+    cfg, kw = GOLDEN_CASES[name][0](), GOLDEN_CASES[name][1]
+    rec = load_golden(name)
+    on_device = kw["source"] in ("greedy", "waiting")
+    for obs_dtype in ("float32", "int8"):
+        got = replay_device(cfg, rec, policy=kw["source"] if on_device else "external", use_order=False,
+                            obs_dtype=obs_dtype, reward_dtype="float32", kernel="threads")
+        assert got["_kernel"] == "threads"
+        assert_same(rec, got, f"threads/{name}/{obs_dtype}", policy_actions=on_device, reward_rtol=1e-6)
+        assert np.array_equal(got["reward"], rec["reward"].astype(np.float32).astype(np.float64)), "rewards are the rounded float64"
+
+
 # ---- seeded comparison against the oracle, every kernel instantiation ----------------------------
 ORACLE_CASES = {
     "A1": (lambda: crew_config(1, 0, max_steps=25), 37),
     "A3_cassette": (cassette_config, 101),
+    "A4": (lambda: crew_config(3, 1, max_steps=40, reward="simple_distance", term="all"), 1000),
     "A5": (lambda: crew_config(3, 2, max_steps=40, term="all"), 258),
     "A8_readme": (lambda: readme_config(max_steps=60), 1031),
     "A12": (lambda: crew_config(7, 5, max_steps=40, reward="simple_distance"), 130),
@@ -78,9 +97,13 @@ def _compare_step(env, orc, res, out, tag, obs_np):
     assert np.array_equal(out.obs.cpu().numpy().astype(obs_np), res["obs"]), f"{tag}: obs"
 
 
+# every case with the default mapping, and the crews the thread-per-env kernel takes also with the lane-group one
+CASE_KERNELS = [(c, "auto") for c in ORACLE_CASES] + [("A4", "lanes"), ("A8_readme", "lanes")]
+
+
 @pytest.mark.parametrize("policy", ["random", "greedy", "waiting"])
-@pytest.mark.parametrize("case", list(ORACLE_CASES))
-def test_device_matches_oracle_with_auto_reset(case, policy):
+@pytest.mark.parametrize("case,kernel", CASE_KERNELS)
+def test_device_matches_oracle_with_auto_reset(case, kernel, policy):
     """Same seeded start states, on-device policy, auto-reset on: every step, every field."""
     import oracle
 
@@ -91,7 +114,9 @@ def test_device_matches_oracle_with_auto_reset(case, policy):
     x, y, f, s = random_states(cfg, n, rng)
     seed, offset = 1234567 + n, 10_000_000_000 + n  # offset > 2**32: both counter words matter
     obs_dtype = "float32" if policy == "greedy" else "int8"
-    env = make_env(cfg, n, seed=seed, global_env_offset=offset, obs_dtype=obs_dtype, auto_reset=True, with_info=True)
+    if case == "A4" and kernel == "auto":
+        obs_dtype = "float32"   # a 4-agent env's int8 block is not a whole number of 16-byte vectors
+    env = make_env(cfg, n, seed=seed, global_env_offset=offset, obs_dtype=obs_dtype, auto_reset=True, with_info=True, kernel=kernel)
     orc = oracle.OracleEnvs(low, n, seed=seed, global_env_offset=offset)
     env.set_state(*(torch.from_numpy(v).cuda() for v in (x, y, f, s)))
     orc.set_state(x, y, f, s)
@@ -101,6 +126,7 @@ def test_device_matches_oracle_with_auto_reset(case, policy):
         res = orc.step(policy=policy, auto_reset=True, obs_dtype=_abi.OBS_FP32 if obs_dtype == "float32" else _abi.OBS_INT8)
         _compare_step(env, orc, res, out, f"{case}/{policy}/t={t}", np.float32 if obs_dtype == "float32" else np.int8)
     env.check_error()
+    assert env.last_kernel == ("threads" if kernel == "auto" and case in ("A4", "A8_readme") else "lanes")
     st, want = env.stats(), orc.stats.as_dict()
     for k in ("env_steps", "episodes", "terminated_all", "truncated_all", "arrivals", "episode_length_sum"):
         assert st[k] == want[k], (k, st[k], want[k])
@@ -135,6 +161,60 @@ def test_device_external_actions_and_custom_order_match_oracle(case):
         res = orc.step(acts, order=order if use_order else None, obs_dtype=_abi.OBS_INT8, reward_dtype=_abi.REWARD_F64)
         _compare_step(env, orc, res, out, f"{case}/t={t}", np.int8)
     env.check_error()
+
+
+@pytest.mark.parametrize("obs_dtype", ["none", "int8", "float32"])
+@pytest.mark.parametrize("case", ["A4", "A8_readme"])
+def test_thread_per_env_kernel_external_actions_match_oracle(case, obs_dtype):
+    """External action tensors (incl. out-of-range values that must raise), no auto-reset, ragged
+    env counts: the thread-per-env kernel against the oracle and against the lane-group kernel."""
+    import oracle
+
+    make_cfg, _ = ORACLE_CASES[case]
+    cfg = make_cfg()
+    low = lower_config(cfg)
+    A = low.num_agents
+    if obs_dtype == "int8" and A != 8:
+        pytest.skip("int8 rows of a 4-agent env are not 16-byte multiples: served by the lane-group kernel")
+    code = {"none": _abi.OBS_NONE, "int8": _abi.OBS_INT8, "float32": _abi.OBS_FP32}[obs_dtype]
+    for n in (1, 31, 33, 517):
+        rng = np.random.default_rng(n)
+        x, y, f, s = random_states(cfg, n, rng, step_hi=low.max_steps - 5)
+        envs = {k: make_env(cfg, n, obs_dtype=obs_dtype, auto_reset=False, with_info=True, kernel=k) for k in ("threads", "lanes")}
+        orc = oracle.OracleEnvs(low, n)
+        for e in envs.values():
+            e.set_state(*(torch.from_numpy(v).cuda() for v in (x, y, f, s)))
+        orc.set_state(x, y, f, s)
+        for t in range(30):
+            acts = rng.integers(0, 5, size=(n, A)).astype(np.int8)
+            res = orc.step(acts, obs_dtype=code)
+            for k, e in envs.items():
+                out = e.step(torch.from_numpy(acts).cuda())
+                assert e.last_kernel == k
+                for name, a, b in (("x", e.x, orc.x), ("y", e.y, orc.y), ("flags", e.flags, orc.flags), ("step", e.step_count, orc.step_count),
+                                   ("episode_return", e.episode_return, orc.episode_return), ("reward", out.reward, res["reward"]),
+                                   ("agent_flags", out.agent_flags, res["agent_flags"]), ("agent_info", out.agent_info, res["agent_info"]),
+                                   ("env_flags", out.env_flags, res["env_flags"])):
+                    assert np.array_equal(a.cpu().numpy(), b), f"{case}/{k}/n={n}/t={t}: {name}"
+                if obs_dtype != "none":
+                    assert np.array_equal(out.obs.cpu().numpy(), res["obs"]), f"{case}/{k}/n={n}/t={t}: obs"
+        for e in envs.values():
+            e.check_error()
+        bad = rng.integers(0, 5, size=(n, A)).astype(np.int8)
+        bad[n - 1, A - 1] = 7
+        envs["threads"].step(torch.from_numpy(bad).cuda())
+        with pytest.raises(ValueError, match="Invalid action"):
+            envs["threads"].check_error()
+        for e in envs.values():
+            e.close()
+
+
+def test_thread_per_env_request_on_ineligible_step_raises():
+    env = make_env(crew_config(3, 2), 8, obs_dtype="none", kernel="threads")
+    env.reset()
+    with pytest.raises(NotImplementedError, match="CC_KERNEL_THREADS"):
+        env.step(policy="greedy")
+    env.close()
 
 
 # ---- BASELINE config 2 at full size: 65,536 envs, greedy policy, bit-exact replay ----------------
