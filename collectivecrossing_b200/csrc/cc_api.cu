@@ -55,6 +55,8 @@ struct cc_handle {
     ccb::Pcg64State *gen = nullptr;  // per-env numpy-compatible generators (allocated on first seeded reset)
     bool gen_seeded = false;
     int64_t launches = 0;
+    unsigned *tpe_counters = nullptr;   // two work counters of the thread-per-env kernel (launch parity)
+    int64_t tpe_launches = 0;
     int variant = CC_KERNEL_AUTO;   // cc_set_kernel_variant
     int last_variant = 0;           // mapping of the last step launch (CC_KERNEL_LANES / CC_KERNEL_THREADS)
     // host-path staging
@@ -155,7 +157,14 @@ int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
     using L = ccb::TpeLayout<A, OBS>;
     auto kern = ccb::cc_step_tpe_kernel<A, OBS>;
     p.n_groups = (h->n_envs + 31) / 32;
-    const int smem = L::kStageBytes;
+    // greedy / waiting: a private lattice bitmap per thread while the lattice is small (README: 6 words)
+    const bool on_device_policy = p.policy == CC_POLICY_GREEDY || p.policy == CC_POLICY_WAITING;
+    p.tpe_bm_words = (on_device_policy && p.walk_words <= ccb::kTpeMaxBitmapWords) ? p.walk_words : 0;
+    // launch k counts its groups in counter k & 1 and zeroes the other one for launch k + 1 (launches of
+    // one handle are stream-ordered by contract)
+    p.tpe_counter = h->tpe_counters + (h->tpe_launches & 1);
+    p.tpe_counter_next = h->tpe_counters + ((h->tpe_launches + 1) & 1);
+    const int smem = L::kStageBytes + p.tpe_bm_words * ccb::kTpeThreads * 4;
     CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
     CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ccb::kTpeThreads, smem));
@@ -167,6 +176,7 @@ int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
     kern<<<grid, ccb::kTpeThreads, smem, s>>>(p);
     CC_CUDA(cudaGetLastError());
     h->launches += 1;
+    h->tpe_launches += 1;
     return CC_OK;
 }
 
@@ -264,7 +274,7 @@ int cc_create(const cc_config *cfg, int64_t n_envs, int device, int64_t global_e
     const size_t na = (size_t)n_envs * A;
     const size_t o_x = 0, o_y = align256(o_x + na), o_f = align256(o_y + na), o_s = align256(o_f + na),
                  o_r = align256(o_s + (size_t)n_envs * 4), o_st = align256(o_r + (size_t)n_envs * 4),
-                 o_e = align256(o_st + ccb::kStCount * 8), total = align256(o_e + 4);
+                 o_e = align256(o_st + ccb::kStCount * 8), o_c = align256(o_e + 4), total = align256(o_c + 8);
     e = cudaMalloc(&h->own_block, total);
     if (e != cudaSuccess) { delete h; return fail(CC_ERR_NOMEM, "cudaMalloc(%zu): %s", total, cudaGetErrorString(e)); }
     cudaMemset(h->own_block, 0, total);
@@ -273,6 +283,7 @@ int cc_create(const cc_config *cfg, int64_t n_envs, int device, int64_t global_e
     h->flags = reinterpret_cast<uint8_t *>(b + o_f); h->step = reinterpret_cast<int32_t *>(b + o_s);
     h->ep_ret = reinterpret_cast<float *>(b + o_r); h->stats = reinterpret_cast<unsigned long long *>(b + o_st);
     h->err = reinterpret_cast<int *>(b + o_e);
+    h->tpe_counters = reinterpret_cast<unsigned *>(b + o_c);
     h->owns_state = true;
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
     *out = h;

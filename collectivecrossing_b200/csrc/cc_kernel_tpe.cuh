@@ -19,11 +19,20 @@
 #ifndef CCB_TPE_MIN_BLOCKS
 #define CCB_TPE_MIN_BLOCKS 3   // resident CTAs per SM the register allocator must allow
 #endif
+#ifndef CCB_TPE_PAIRWISE
+#define CCB_TPE_PAIRWISE 1     // float32 rows: lane <-> pair (conflict-free 8-byte gathers and stores) instead of lane <-> 16-byte vector
+#endif
+#ifndef CCB_TPE_DYNAMIC
+#define CCB_TPE_DYNAMIC 1      // warps take their next group of 32 envs from an atomic counter (no tail round, ascending writes)
+#endif
 
 namespace ccb {
 
 constexpr int kTpeWarps = 8;
 constexpr int kTpeThreads = kTpeWarps * 32;
+constexpr int kTpeMaxBitmapWords = 16;   // private policy bitmaps up to 512 padded lattice points (16 KB per CTA)
+
+constexpr int tpe_gcd(int a, int b) { return b == 0 ? a : tpe_gcd(b, a % b); }
 
 template <int A, int OBS>
 struct TpeLayout {
@@ -44,7 +53,18 @@ struct TpeLayout {
     static constexpr int TSB = (((TPL_PAIRS * PSZ + UNIT - 1) / UNIT) | 1) * UNIT;
     static constexpr int kStageBytesPerWarp = kHasObs ? 32 * TSB : 0;
     static constexpr int kStageBytes = kTpeWarps * kStageBytesPerWarp;
-    static constexpr int kLutWords = kHasObs ? VPE * PPV / 2 : 1;   // two 16-bit template offsets per word
+    // Emission: the 32 envs of a warp are NB blocks of EB envs; a block is a whole number (JB) of
+    // 32-vector rows, so vector j of lane l lies at the same place of every block and ONE table entry
+    // per (j, lane) — the offsets of its source pairs from the block's first template — serves all blocks.
+    // With kPairwise (float32) the unit is an 8-byte pair instead of a 16-byte vector: a warp
+    // instruction then gathers 32 CONSECUTIVE output pairs, which are (but for the own position and
+    // the masked block) consecutive template pairs — no bank conflicts — and stores 256 contiguous bytes.
+    static constexpr bool kPairwise = OBS == CC_OBS_FP32 && CCB_TPE_PAIRWISE != 0;
+    static constexpr int UPE = kPairwise ? PPE : VPE;    // emission units (pairs or vectors) per env
+    static constexpr int G = tpe_gcd(UPE > 0 ? UPE : 1, 32);
+    static constexpr int NB = G, EB = 32 / G, JB = UPE / G;
+    static constexpr int kLutEntryWords = kPairwise ? 1 : (OBS == CC_OBS_FP32 ? 2 : 4);   // 1 or 2 x 32-bit, or 8 x 16-bit offsets
+    static constexpr int kLutWords = kHasObs ? JB * 32 * kLutEntryWords : 4;
 };
 
 // byte offset, inside an env's row template, of the pair that feeds output pair q of row i
@@ -57,6 +77,13 @@ __device__ __forceinline__ unsigned tpe_template_offset(int i, int q) {
     else if (q == 2) idx = 2 * A + 1;
     else idx = ((q - 3) >> 1) == i ? 2 * A + 2 : q - 3;
     return (unsigned)(idx * PSZ);
+}
+
+// same, for output pair P (0 .. A*R-1) of an env
+template <int A, int PSZ>
+__device__ __forceinline__ unsigned tpe_pair_offset(int P) {
+    constexpr int R = 3 + 2 * A;
+    return tpe_template_offset<A, PSZ>(P / R, P % R);
 }
 
 // A bytes of env `env` of an [N][A] byte array as one word per thread where A allows it
@@ -109,9 +136,10 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     __shared__ float rtab[2 * kRtabSize];
     __shared__ uint8_t act_tab[kPolicyRows * 16];
     __shared__ unsigned long long red_all[kTpeWarps * kStCount];
-    __shared__ __align__(16) unsigned lut[L::kLutWords];
+    __shared__ __align__(16) unsigned lut[L::kLutWords];   // emission table, see TpeLayout
     unsigned char *wstage = smem + warp * L::kStageBytesPerWarp;   // this warp's 32 templates
     unsigned char *tpl = wstage + lane * L::TSB;                    // this thread's env
+    unsigned *bm = reinterpret_cast<unsigned *>(smem + L::kStageBytes) + threadIdx.x;   // private lattice bitmap (policies)
 
     // ---- once per CTA: tables (same contents as cc_kernels.cuh) -------------------------------------
     for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
@@ -140,8 +168,13 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     }
     if (kHasObs) {
         for (int w = threadIdx.x; w < L::kLutWords; w += blockDim.x) {
-            const int P0 = 2 * w, P1 = 2 * w + 1;   // consecutive output pairs of an env
-            lut[w] = tpe_template_offset<A, L::PSZ>(P0 / L::R, P0 % L::R) | (tpe_template_offset<A, L::PSZ>(P1 / L::R, P1 % L::R) << 16);
+            // entry (j, lane) describes vector v = lane + 32 j of a block: env e = v / VPE, vector r = v % VPE of that env
+            const int entry = w / L::kLutEntryWords, part = w % L::kLutEntryWords;
+            const int v = (entry & 31) + 32 * (entry >> 5), e = v / L::UPE, r = v % L::UPE;
+            if (L::kPairwise) lut[w] = (unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(r);
+            else if (OBS == CC_OBS_FP32) lut[w] = (unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(2 * r + part);
+            else lut[w] = ((unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(8 * r + 2 * part)) |
+                          (((unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(8 * r + 2 * part + 1)) << 16);
         }
         // the constant pairs of this thread's template
         P2 *t = reinterpret_cast<P2 *>(tpl);
@@ -149,6 +182,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     }
     unsigned long long *red = red_all + warp * kStCount;
     if (lane < kStCount) red[lane] = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.tpe_counter_next = 0u;   // the counter the NEXT launch uses
     __syncthreads();
     unsigned st_arrivals = 0;
     double st_rsum = 0.0;
@@ -156,7 +190,18 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
 
     const int total_warps = (int)gridDim.x * kTpeWarps;
     const int n_groups = (int)p.n_groups;   // groups of 32 envs
-    for (int g = (int)blockIdx.x * kTpeWarps + warp; g < n_groups; g += total_warps) {
+    // Work distribution: every warp starts on group (its global index); later groups come from an
+    // atomic counter, fetched one iteration ahead so that the round trip is hidden.  Compared with a
+    // fixed stride this has no partially filled last round, and the groups in flight stay a compact,
+    // ascending window of the output (profiles/probes/store_pattern_probe.cu: 6.2 -> 6.9 TB/s).
+    int g = (int)blockIdx.x * kTpeWarps + warp;
+    int g_next = 0;
+    for (; g < n_groups; g = g_next) {
+#if CCB_TPE_DYNAMIC
+        if (lane == 0) g_next = total_warps + (int)atomicAdd(p.tpe_counter, 1u);
+#else
+        g_next = g + total_warps;
+#endif
         const int n = g * 32 + lane;
         const int envs_here = (int)min(32ll, p.n_envs - (long long)g * 32);
         const bool env_ok = lane < envs_here;                 // false only in the ragged last group
@@ -182,7 +227,9 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         int cell[A];
         unsigned geo_u[A], geo_f[A];
         auto lookup = [&](int k) {
-            const int cx = min((int)(pos[k] >> 8), p.W + 1) + 1, cy = min((int)(pos[k] & 0xffu), p.H + 1) + 1;
+            // (clamped to the lattice: set_state promises in-lattice positions, the clamp only keeps the
+            // table and bitmap reads of garbage in bounds — all four neighbours lie in the padded lattice)
+            const int cx = min((int)(pos[k] >> 8), p.W) + 1, cy = min((int)(pos[k] & 0xffu), p.H) + 1;
             const unsigned xv = xt[cx], yv = yt[(k < p.B ? 0 : kMaxPad) + cy];
             cell[k] = cy * PW + cx;
             geo_u[k] = yv + xv;
@@ -218,18 +265,39 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
                 pending |= k >= p.B && (fl[k] & 6u) == 0u && env_ok && !(geo_f[k] & 8u);
             }
             const bool exiting_pending = p.policy == CC_POLICY_WAITING && pending;
+            // validity of the four moves of every agent (greedy_policy.py:238-264 -> _is_move_valid,
+            // collectivecrossing.py:345-369): a walkable target that no ACTIVE agent holds (the asking
+            // agent's own cell is never one of its targets)
+            unsigned vmask[A];
+            if (p.tpe_bm_words > 0) {
+                // small lattice: the thread keeps a private bitmap "wall or occupied" of the padded
+                // lattice in shared memory (word w at bm[w * kTpeThreads]: a thread only ever touches
+                // its own bank), so a move is valid iff ONE bit is clear
+                for (int w = 0; w < p.tpe_bm_words; ++w) bm[w * kTpeThreads] = ~walk[w];
+#pragma unroll
+                for (int k = 0; k < A; ++k)
+                    if (fl[k] & CC_F_ACTIVE) bm[(cell[k] >> 5) * kTpeThreads] |= 1u << (cell[k] & 31);
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    const int c = cell[k];
+                    auto blocked = [&](int idx) { return (bm[(idx >> 5) * kTpeThreads] >> (idx & 31)) & 1u; };
+                    vmask[k] = (blocked(c + 1) | (blocked(c + PW) << 1) | (blocked(c - 1) << 2) | (blocked(c - PW) << 3)) ^ 15u;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    const int c = cell[k];
+                    const unsigned q = pos[k];
+                    const unsigned v0 = walkable(c + 1) & (unsigned)!occupied((q + 0x100u) & 0xffffu);
+                    const unsigned v1 = walkable(c + PW) & (unsigned)!occupied((q + 1u) & 0xffffu);
+                    const unsigned v2 = walkable(c - 1) & (unsigned)!occupied((q - 0x100u) & 0xffffu);
+                    const unsigned v3 = walkable(c - PW) & (unsigned)!occupied((q - 1u) & 0xffffu);
+                    vmask[k] = v0 | (v1 << 1) | (v2 << 2) | (v3 << 3);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < A; ++k) {
-                // validity of the four moves (greedy_policy.py:238-264 -> _is_move_valid, :345-369):
-                // walkable target that no ACTIVE agent holds (the asking agent's own cell is never a target)
-                const int c = cell[k];
-                const unsigned q = pos[k];
-                const unsigned v0 = walkable(c + 1) & (unsigned)!occupied((q + 0x100u) & 0xffffu);
-                const unsigned v1 = walkable(c + PW) & (unsigned)!occupied((q + 1u) & 0xffffu);
-                const unsigned v2 = walkable(c - 1) & (unsigned)!occupied((q - 0x100u) & 0xffffu);
-                const unsigned v3 = walkable(c - PW) & (unsigned)!occupied((q - 1u) & 0xffffu);
-                const unsigned vmask = v0 | (v1 << 1) | (v2 << 2) | (v3 << 3);
-                const unsigned a = act_tab[((geo_u[k] & 0xffu) << 4) | vmask];
+                const unsigned a = act_tab[((geo_u[k] & 0xffu) << 4) | vmask[k]];
                 const bool asks = (fl[k] & 7u) == CC_F_ACTIVE;                         // active, not done
                 const bool waits = exiting_pending && k < p.B && !(geo_f[k] & 1u);    // waiting_policy.py:74-108
                 action[k] = (asks && !waits) ? a : (unsigned)CC_ACT_WAIT;
@@ -405,37 +473,60 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             }
             __syncwarp();
             uint4 *outv = reinterpret_cast<uint4 *>(p.obs) + (size_t)g * 32 * L::VPE + lane;
-            const unsigned char *tb = wstage;   // template of the env the lane's current vector belongs to
-            int r = lane;                       // vector index inside that env
-            while (r >= L::VPE) { r -= L::VPE; tb += L::TSB; }
-            auto emit = [&](uint4 *dst) {
-                uint4 o;
-                if constexpr (OBS == CC_OBS_FP32) {
-                    const unsigned l = lut[r];
-                    const float2 a = *reinterpret_cast<const float2 *>(tb + (l & 0xffffu));
-                    const float2 b = *reinterpret_cast<const float2 *>(tb + (l >> 16));
-                    o = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(b.x), __float_as_uint(b.y));
-                } else {
-                    const uint4 l = reinterpret_cast<const uint4 *>(lut)[r];
-                    auto two = [&](unsigned w) {
-                        return (unsigned)*reinterpret_cast<const unsigned short *>(tb + (w & 0xffffu)) |
-                               ((unsigned)*reinterpret_cast<const unsigned short *>(tb + (w >> 16)) << 16);
-                    };
-                    o = make_uint4(two(l.x), two(l.y), two(l.z), two(l.w));
-                }
-                __stcs(dst, o);
-                r += 32;
-                while (r >= L::VPE) { r -= L::VPE; tb += L::TSB; }
-            };
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(wstage);
             if (envs_here == 32) {
-#pragma unroll 4
-                for (int j = 0; j < L::VPE; ++j) emit(outv + 32 * j);    // 32 envs x VPE vectors = VPE per lane
+#pragma unroll
+                for (int j = 0; j < L::JB; ++j) {
+                    if constexpr (L::kPairwise) {
+                        const unsigned a0 = sbase + lut[j * 32 + lane];
+                        uint2 *outp = reinterpret_cast<uint2 *>(p.obs) + (size_t)g * 32 * L::PPE + lane;
+#pragma unroll
+                        for (int b = 0; b < L::NB; ++b) {
+                            uint2 o;
+                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(a0 + (unsigned)(b * L::EB * L::TSB)));
+                            __stcs(outp + b * L::EB * L::PPE + 32 * j, o);
+                        }
+                    } else if constexpr (OBS == CC_OBS_FP32) {
+                        const uint2 d = reinterpret_cast<const uint2 *>(lut)[j * 32 + lane];
+                        const unsigned a0 = sbase + d.x, a1 = sbase + d.y;
+#pragma unroll
+                        for (int b = 0; b < L::NB; ++b) {
+                            uint4 o;
+                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(a0 + (unsigned)(b * L::EB * L::TSB)));
+                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.z), "=r"(o.w) : "r"(a1 + (unsigned)(b * L::EB * L::TSB)));
+                            __stcs(outv + b * L::EB * L::VPE + 32 * j, o);
+                        }
+                    } else {
+                        const uint4 d = reinterpret_cast<const uint4 *>(lut)[j * 32 + lane];
+#pragma unroll
+                        for (int b = 0; b < L::NB; ++b) {
+                            auto two = [&](unsigned w) {
+                                unsigned short lo, hi;
+                                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(sbase + (w & 0xffffu) + (unsigned)(b * L::EB * L::TSB)));
+                                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(sbase + (w >> 16) + (unsigned)(b * L::EB * L::TSB)));
+                                return (unsigned)lo | ((unsigned)hi << 16);
+                            };
+                            __stcs(outv + b * L::EB * L::VPE + 32 * j, make_uint4(two(d.x), two(d.y), two(d.z), two(d.w)));
+                        }
+                    }
+                }
             } else {
+                // ragged last group of a launch: plain index arithmetic, at most one warp per launch
                 const int nvec = envs_here * L::VPE;
-                for (int v = lane; v < nvec; v += 32) emit(outv + (v - lane));
+                for (int v = lane; v < nvec; v += 32) {
+                    const int e = v / L::VPE, r = v % L::VPE;
+                    const unsigned char *tb = wstage + e * L::TSB;
+                    union { uint4 u; P2 q[L::PPV]; } o;
+#pragma unroll
+                    for (int c = 0; c < L::PPV; ++c) o.q[c] = *reinterpret_cast<const P2 *>(tb + tpe_pair_offset<A, L::PSZ>(L::PPV * r + c));
+                    __stcs(outv + (v - lane), o.u);
+                }
             }
             __syncwarp();
         }
+#if CCB_TPE_DYNAMIC
+        g_next = __shfl_sync(kFull, g_next, 0);
+#endif
     }
 
     // ---- statistics: per-warp slots in shared memory -> one atomic per slot per CTA ----------------

@@ -68,6 +68,8 @@ struct KParams {
     unsigned reward_category_mask;  // 0xF for the default reward (category overrides apply), else 0
     long long n_groups;
     int smem_total;
+    int tpe_bm_words;    // thread-per-env kernel: words of the private lattice bitmap (0 = compare-based occupancy)
+    unsigned *tpe_counter, *tpe_counter_next;   // thread-per-env kernel: work counters of this / the next launch
 };
 
 // ---------------------------------------------------------------------------------------------
