@@ -19,9 +19,6 @@
 #ifndef CCB_TPE_MIN_BLOCKS
 #define CCB_TPE_MIN_BLOCKS 3   // resident CTAs per SM the register allocator must allow
 #endif
-#ifndef CCB_TPE_PAIRWISE
-#define CCB_TPE_PAIRWISE 1     // float32 rows: lane <-> pair (conflict-free 8-byte gathers and stores) instead of lane <-> 16-byte vector
-#endif
 #ifndef CCB_TPE_DYNAMIC
 #define CCB_TPE_DYNAMIC 1      // warps take their next group of 32 envs from an atomic counter (no tail round, ascending writes)
 #endif
@@ -45,46 +42,52 @@ struct TpeLayout {
     static constexpr int PPV = 16 / PSZ;                 // pairs per 16-byte vector
     static constexpr bool kVectorisable = PPE % PPV == 0;
     static constexpr int VPE = PPE / PPV;                // 16-byte vectors per env
-    // row template of one env: [S_0a, S_0b, ..., S_(A-1)a, S_(A-1)b, K1, K2, M]  (2A+3 pairs); its
-    // stride is an ODD number of store units (16 B for float32, 4 B for int8) so that the 32 threads
-    // of a warp write their templates without bank conflicts
-    static constexpr int TPL_PAIRS = 2 * A + 3;
+    // Row template of one env in shared memory.
+    //   float32: [S_0a, S_0b, ..., S_(A-1)a, S_(A-1)b] — the agent table only (2A pairs of 8 bytes); the
+    //            constant pairs K1, K2, M never touch shared memory (they are selected from registers);
+    //   int8:    [S_0a, ..., S_(A-1)b, K1, K2, M] (2A+3 pairs of 2 bytes).
+    // The stride is an ODD number of store units (16 B for float32, 4 B for int8) so that the 32 threads
+    // of a warp write their templates without bank conflicts.
+    static constexpr int TPL_PAIRS = OBS == CC_OBS_FP32 ? 2 * A : 2 * A + 3;
     static constexpr int UNIT = OBS == CC_OBS_FP32 ? 16 : 4;
     static constexpr int TSB = (((TPL_PAIRS * PSZ + UNIT - 1) / UNIT) | 1) * UNIT;
     static constexpr int kStageBytesPerWarp = kHasObs ? 32 * TSB : 0;
     static constexpr int kStageBytes = kTpeWarps * kStageBytesPerWarp;
     // Emission: the 32 envs of a warp are NB blocks of EB envs; a block is a whole number (JB) of
-    // 32-vector rows, so vector j of lane l lies at the same place of every block and ONE table entry
-    // per (j, lane) — the offsets of its source pairs from the block's first template — serves all blocks.
-    // With kPairwise (float32) the unit is an 8-byte pair instead of a 16-byte vector: a warp
-    // instruction then gathers 32 CONSECUTIVE output pairs, which are (but for the own position and
-    // the masked block) consecutive template pairs — no bank conflicts — and stores 256 contiguous bytes.
-    static constexpr bool kPairwise = OBS == CC_OBS_FP32 && CCB_TPE_PAIRWISE != 0;
-    static constexpr int UPE = kPairwise ? PPE : VPE;    // emission units (pairs or vectors) per env
+    // 32-unit rows, so unit j of lane l lies at the same place of every block and ONE table entry per
+    // (j, lane) — the offset of its source from the block's first template — serves all blocks.
+    //   float32: unit = one 8-byte pair (lane <-> pair).  A warp instruction gathers 32 CONSECUTIVE output
+    //            pairs; but for the own position these are consecutive template pairs or constants, so
+    //            the gather is free of bank conflicts inside an env, and it stores 256 contiguous bytes
+    //            (measured against 16-byte vectors assembled from two gathers: 2-way conflicts on every load).
+    //   int8:    unit = one 16-byte vector of 8 pairs.
+    static constexpr bool kPairwise = OBS == CC_OBS_FP32;
+    static constexpr int UPE = kPairwise ? PPE : VPE;    // emission units per env
     static constexpr int G = tpe_gcd(UPE > 0 ? UPE : 1, 32);
     static constexpr int NB = G, EB = 32 / G, JB = UPE / G;
-    static constexpr int kLutEntryWords = kPairwise ? 1 : (OBS == CC_OBS_FP32 ? 2 : 4);   // 1 or 2 x 32-bit, or 8 x 16-bit offsets
+    static constexpr int kLutEntryWords = kPairwise ? 1 : 4;   // one coded source, or 8 x 16-bit offsets
     static constexpr int kLutWords = kHasObs ? JB * 32 * kLutEntryWords : 4;
 };
 
-// byte offset, inside an env's row template, of the pair that feeds output pair q of row i
-// (observations.py:62-94: own position, door constants, then every agent's block with the own block masked)
-template <int A, int PSZ>
-__device__ __forceinline__ unsigned tpe_template_offset(int i, int q) {
-    int idx;
-    if (q == 0) idx = 2 * i;
-    else if (q == 1) idx = 2 * A;
-    else if (q == 2) idx = 2 * A + 1;
-    else idx = ((q - 3) >> 1) == i ? 2 * A + 2 : q - 3;
-    return (unsigned)(idx * PSZ);
+// Source of output pair q of row i (observations.py:62-94: own position, door constants, then every
+// agent's block with the own block masked): index of a pair of the agent table S (>= 0), or one of the
+// constant pairs.
+enum { kSrcK1 = -1, kSrcK2 = -2, kSrcM = -3 };
+template <int A>
+__device__ __forceinline__ int tpe_source(int i, int q) {
+    if (q == 0) return 2 * i;                     // (x_i, y_i) = S_ia
+    if (q == 1) return kSrcK1;                    // (door centre, division)
+    if (q == 2) return kSrcK2;                    // (door left, door right)
+    return ((q - 3) >> 1) == i ? kSrcM : q - 3;   // (-1, -1) over the own block
 }
-
-// same, for output pair P (0 .. A*R-1) of an env
+// int8 template: byte offset of the pair feeding output pair P (0 .. A*R-1) of an env; constants follow the table
 template <int A, int PSZ>
 __device__ __forceinline__ unsigned tpe_pair_offset(int P) {
     constexpr int R = 3 + 2 * A;
-    return tpe_template_offset<A, PSZ>(P / R, P % R);
+    const int src = tpe_source<A>(P / R, P % R);
+    return (unsigned)((src >= 0 ? src : 2 * A - 1 - src) * PSZ);
 }
+constexpr unsigned kLutConstShift = 30;   // float32 table entries: bits 31-30 = 0 load / 1 K1 / 2 K2 / 3 M
 
 // A bytes of env `env` of an [N][A] byte array as one word per thread where A allows it
 template <int A>
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     constexpr bool kHasObs = L::kHasObs;
     constexpr unsigned kGhost = 0xFFFFFFFFu;
     static_assert(A >= 1 && A <= 8, "thread-per-env mapping is for crews of at most 8");
-    static_assert(!kHasObs || L::kVectorisable, "an env's observation block must be a whole number of 16-byte vectors");
+    static_assert(OBS != CC_OBS_INT8 || L::kVectorisable, "an env's observation block must be a whole number of 16-byte vectors");
     extern __shared__ __align__(16) unsigned char smem[];   // row templates: [warp][32 envs][TSB]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -168,18 +171,26 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     }
     if (kHasObs) {
         for (int w = threadIdx.x; w < L::kLutWords; w += blockDim.x) {
-            // entry (j, lane) describes vector v = lane + 32 j of a block: env e = v / VPE, vector r = v % VPE of that env
+            // entry (j, lane) describes unit v = lane + 32 j of a block: env e = v / UPE, unit r = v % UPE of that env
             const int entry = w / L::kLutEntryWords, part = w % L::kLutEntryWords;
             const int v = (entry & 31) + 32 * (entry >> 5), e = v / L::UPE, r = v % L::UPE;
-            if (L::kPairwise) lut[w] = (unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(r);
-            else if (OBS == CC_OBS_FP32) lut[w] = (unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(2 * r + part);
-            else lut[w] = ((unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(8 * r + 2 * part)) |
-                          (((unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(8 * r + 2 * part + 1)) << 16);
+            if (L::kPairwise) {
+                const int src = tpe_source<A>(r / L::R, r % L::R);
+                lut[w] = src >= 0 ? (unsigned)(e * L::TSB + src * L::PSZ) : ((unsigned)(-src) << kLutConstShift);
+            } else {
+                lut[w] = ((unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(8 * r + 2 * part)) |
+                         (((unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(8 * r + 2 * part + 1)) << 16);
+            }
         }
-        // the constant pairs of this thread's template
-        P2 *t = reinterpret_cast<P2 *>(tpl);
-        t[2 * A] = mk_pair<OT>(p.DC, p.D); t[2 * A + 1] = mk_pair<OT>(p.DL, p.DR); t[2 * A + 2] = mk_pair<OT>(-1, -1);
+        if (OBS == CC_OBS_INT8) {   // the constant pairs of this thread's template
+            P2 *t = reinterpret_cast<P2 *>(tpl);
+            t[2 * A] = mk_pair<OT>(p.DC, p.D); t[2 * A + 1] = mk_pair<OT>(p.DL, p.DR); t[2 * A + 2] = mk_pair<OT>(-1, -1);
+        }
     }
+    // float32 rows: the constant pairs as register values
+    const uint2 kc1 = make_uint2(__float_as_uint((float)p.DC), __float_as_uint((float)p.D));
+    const uint2 kc2 = make_uint2(__float_as_uint((float)p.DL), __float_as_uint((float)p.DR));
+    const uint2 kcm = make_uint2(__float_as_uint(-1.f), __float_as_uint(-1.f));
     unsigned long long *red = red_all + warp * kStCount;
     if (lane < kStCount) red[lane] = 0ull;
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.tpe_counter_next = 0u;   // the counter the NEXT launch uses
@@ -472,31 +483,39 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
                     reinterpret_cast<unsigned *>(tpl)[k] = (pos[k] >> 8) | ((pos[k] & 0xffu) << 8) | ((k < p.B ? 0u : 1u) << 16) | ((fl[k] & 1u) << 24);
             }
             __syncwarp();
-            uint4 *outv = reinterpret_cast<uint4 *>(p.obs) + (size_t)g * 32 * L::VPE + lane;
             const unsigned sbase = (unsigned)__cvta_generic_to_shared(wstage);
-            if (envs_here == 32) {
+            if constexpr (L::kPairwise) {
+                uint2 *outp = reinterpret_cast<uint2 *>(p.obs) + (size_t)g * 32 * L::PPE + lane;
+                if (envs_here == 32) {
 #pragma unroll
-                for (int j = 0; j < L::JB; ++j) {
-                    if constexpr (L::kPairwise) {
-                        const unsigned a0 = sbase + lut[j * 32 + lane];
-                        uint2 *outp = reinterpret_cast<uint2 *>(p.obs) + (size_t)g * 32 * L::PPE + lane;
+                    for (int j = 0; j < L::JB; ++j) {
+                        const unsigned d = lut[j * 32 + lane], code = d >> kLutConstShift;
+                        const unsigned a0 = sbase + d;                     // (unused when code != 0)
+                        const uint2 cv = code == 1 ? kc1 : (code == 2 ? kc2 : kcm);
 #pragma unroll
                         for (int b = 0; b < L::NB; ++b) {
-                            uint2 o;
-                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(a0 + (unsigned)(b * L::EB * L::TSB)));
+                            uint2 o;   // constant lanes keep their register value: they make no shared-memory access
+                            asm volatile("{\n\t.reg .pred pc;\n\tsetp.ne.u32 pc, %3, 0;\n\tmov.b32 %0, %4;\n\tmov.b32 %1, %5;\n\t"
+                                         "@!pc ld.shared.v2.b32 {%0, %1}, [%2];\n\t}"
+                                         : "=&r"(o.x), "=&r"(o.y) : "r"(a0 + (unsigned)(b * L::EB * L::TSB)), "r"(code), "r"(cv.x), "r"(cv.y));
                             __stcs(outp + b * L::EB * L::PPE + 32 * j, o);
                         }
-                    } else if constexpr (OBS == CC_OBS_FP32) {
-                        const uint2 d = reinterpret_cast<const uint2 *>(lut)[j * 32 + lane];
-                        const unsigned a0 = sbase + d.x, a1 = sbase + d.y;
+                    }
+                } else {
+                    // ragged last group of a launch: plain index arithmetic, at most one warp per launch
+                    const int npair = envs_here * L::PPE;
+                    for (int v = lane; v < npair; v += 32) {
+                        const int e = v / L::PPE, r = v % L::PPE, src = tpe_source<A>(r / L::R, r % L::R);
+                        uint2 o = src == kSrcK1 ? kc1 : (src == kSrcK2 ? kc2 : kcm);
+                        if (src >= 0) o = *reinterpret_cast<const uint2 *>(wstage + e * L::TSB + src * L::PSZ);
+                        __stcs(outp + (v - lane), o);
+                    }
+                }
+            } else {
+                uint4 *outv = reinterpret_cast<uint4 *>(p.obs) + (size_t)g * 32 * L::VPE + lane;
+                if (envs_here == 32) {
 #pragma unroll
-                        for (int b = 0; b < L::NB; ++b) {
-                            uint4 o;
-                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(a0 + (unsigned)(b * L::EB * L::TSB)));
-                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.z), "=r"(o.w) : "r"(a1 + (unsigned)(b * L::EB * L::TSB)));
-                            __stcs(outv + b * L::EB * L::VPE + 32 * j, o);
-                        }
-                    } else {
+                    for (int j = 0; j < L::JB; ++j) {
                         const uint4 d = reinterpret_cast<const uint4 *>(lut)[j * 32 + lane];
 #pragma unroll
                         for (int b = 0; b < L::NB; ++b) {
@@ -509,17 +528,16 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
                             __stcs(outv + b * L::EB * L::VPE + 32 * j, make_uint4(two(d.x), two(d.y), two(d.z), two(d.w)));
                         }
                     }
-                }
-            } else {
-                // ragged last group of a launch: plain index arithmetic, at most one warp per launch
-                const int nvec = envs_here * L::VPE;
-                for (int v = lane; v < nvec; v += 32) {
-                    const int e = v / L::VPE, r = v % L::VPE;
-                    const unsigned char *tb = wstage + e * L::TSB;
-                    union { uint4 u; P2 q[L::PPV]; } o;
+                } else {
+                    const int nvec = envs_here * L::VPE;
+                    for (int v = lane; v < nvec; v += 32) {
+                        const int e = v / L::VPE, r = v % L::VPE;
+                        const unsigned char *tb = wstage + e * L::TSB;
+                        union { uint4 u; P2 q[L::PPV]; } o;
 #pragma unroll
-                    for (int c = 0; c < L::PPV; ++c) o.q[c] = *reinterpret_cast<const P2 *>(tb + tpe_pair_offset<A, L::PSZ>(L::PPV * r + c));
-                    __stcs(outv + (v - lane), o.u);
+                        for (int c = 0; c < L::PPV; ++c) o.q[c] = *reinterpret_cast<const P2 *>(tb + tpe_pair_offset<A, L::PSZ>(L::PPV * r + c));
+                        __stcs(outv + (v - lane), o.u);
+                    }
                 }
             }
             __syncwarp();

@@ -146,6 +146,12 @@ int main() {
     int *counter; cudaMalloc(&counter, 4);
     report("P6 persistent dynamic (atomic counter) cs, 3 CTAs/SM", time_ms([&] { cudaMemsetAsync(counter, 0, 4); p_chunks_dyn<kCs><<<sms * 3, 256>>>(out, n_chunks, counter); }));
     report("P6 persistent dynamic (atomic counter) cs, 6 CTAs/SM", time_ms([&] { cudaMemsetAsync(counter, 0, 4); p_chunks_dyn<kCs><<<sms * 6, 256>>>(out, n_chunks, counter); }));
+    for (int thr : {32, 64, 128, 256, 512})
+        for (int cps : {1, 2}) {
+            char nm[128];
+            snprintf(nm, sizeof nm, "P6 dynamic cs, %d CTA/SM x %d threads (%d storing warps/SM)", cps, thr, cps * thr / 32);
+            report(nm, time_ms([&] { cudaMemsetAsync(counter, 0, 4); p_chunks_dyn<kCs><<<sms * cps, thr>>>(out, n_chunks, counter); }));
+        }
     report("P1 non-persistent 128-thread CTAs cs", time_ms([&] { p_chunks<kCs, 1><<<n_chunks / 4, 128>>>(out, n_chunks); }));
     report("P1 non-persistent 512-thread CTAs cs", time_ms([&] { p_chunks<kCs, 1><<<n_chunks / 16, 512>>>(out, n_chunks); }));
     cudaError_t e = cudaDeviceSynchronize();
