@@ -19,6 +19,12 @@
 #ifndef CCB_TPE_MIN_BLOCKS
 #define CCB_TPE_MIN_BLOCKS 3   // resident CTAs per SM the register allocator must allow
 #endif
+#ifndef CCB_TPE_TMA
+#define CCB_TPE_TMA 1          // float32 rows leave the SM through cp.async.bulk (TMA) instead of st.global, see DESIGN.md §3
+#endif
+#ifndef CCB_TPE_STAGGER_NS
+#define CCB_TPE_STAGGER_NS 0
+#endif
 #ifndef CCB_TPE_DYNAMIC
 #define CCB_TPE_DYNAMIC 1      // warps take their next group of 32 envs from an atomic counter (no tail round, ascending writes)
 #endif
@@ -42,16 +48,23 @@ struct TpeLayout {
     static constexpr int PPV = 16 / PSZ;                 // pairs per 16-byte vector
     static constexpr bool kVectorisable = PPE % PPV == 0;
     static constexpr int VPE = PPE / PPV;                // 16-byte vectors per env
-    // Row template of one env in shared memory.
-    //   float32: [S_0a, S_0b, ..., S_(A-1)a, S_(A-1)b] — the agent table only (2A pairs of 8 bytes); the
-    //            constant pairs K1, K2, M never touch shared memory (they are selected from registers);
-    //   int8:    [S_0a, ..., S_(A-1)b, K1, K2, M] (2A+3 pairs of 2 bytes).
-    // The stride is an ODD number of store units (16 B for float32, 4 B for int8) so that the 32 threads
-    // of a warp write their templates without bank conflicts.
-    static constexpr int TPL_PAIRS = OBS == CC_OBS_FP32 ? 2 * A : 2 * A + 3;
-    static constexpr int UNIT = OBS == CC_OBS_FP32 ? 16 : 4;
-    static constexpr int TSB = (((TPL_PAIRS * PSZ + UNIT - 1) / UNIT) | 1) * UNIT;
-    static constexpr int kStageBytesPerWarp = kHasObs ? 32 * TSB : 0;
+    // Row template of one env in shared memory: [S_0a, S_0b, ..., S_(A-1)a, S_(A-1)b, K1, K2, M], 2A+3 pairs.
+    //   float32: 8-byte pairs, stride exactly 2A+3 pairs (an odd number of 8-byte units), written with
+    //            8-byte stores: the 16 threads of a half-warp then hit 16 distinct bank pairs;
+    //   int8:    2-byte pairs, stride an odd number of 4-byte words, written with 4-byte stores.
+    // The constant pairs K1, K2, M are written once per kernel.
+    static constexpr int TPL_PAIRS = 2 * A + 3;
+    static constexpr int TSB = OBS == CC_OBS_FP32 ? TPL_PAIRS * 8 : (((TPL_PAIRS * PSZ + 3) / 4) | 1) * 4;
+    // float32 rows are assembled env by env in a ring of kImgRing shared-memory images of one env's
+    // observation block (A rows = kImgBytes) and leave the SM as bulk asynchronous copies (TMA): stores
+    // issued with st.global stall the whole load/store pipe of the SM while HBM pushes back, and with it
+    // the shared-memory work of the warps that are stepping envs (profiles/probes/lsu_coupling_probe.cu)
+    static constexpr bool kTma = OBS == CC_OBS_FP32 && CCB_TPE_TMA != 0;
+    static constexpr int kImgBytes = PPE * PSZ;          // 1216 B for A = 8; a multiple of 16 whenever A is even
+    static constexpr int kImgRing = 2;
+    static constexpr int kImgInstr = (PPE + 31) / 32;    // warp instructions that cover an env's pairs
+    static constexpr int kTplBytesPerWarp = kHasObs ? (32 * TSB + 15) / 16 * 16 : 0;
+    static constexpr int kStageBytesPerWarp = kTplBytesPerWarp + (kTma ? kImgRing * kImgBytes : 0);
     static constexpr int kStageBytes = kTpeWarps * kStageBytesPerWarp;
     // Emission: the 32 envs of a warp are NB blocks of EB envs; a block is a whole number (JB) of
     // 32-unit rows, so unit j of lane l lies at the same place of every block and ONE table entry per
@@ -66,7 +79,7 @@ struct TpeLayout {
     static constexpr int G = tpe_gcd(UPE > 0 ? UPE : 1, 32);
     static constexpr int NB = G, EB = 32 / G, JB = UPE / G;
     static constexpr int kLutEntryWords = kPairwise ? 1 : 4;   // one coded source, or 8 x 16-bit offsets
-    static constexpr int kLutWords = kHasObs ? JB * 32 * kLutEntryWords : 4;
+    static constexpr int kLutWords = kHasObs ? (kTma ? kImgInstr * 32 : JB * 32 * kLutEntryWords) : 4;
 };
 
 // Source of output pair q of row i (observations.py:62-94: own position, door constants, then every
@@ -87,7 +100,6 @@ __device__ __forceinline__ unsigned tpe_pair_offset(int P) {
     const int src = tpe_source<A>(P / R, P % R);
     return (unsigned)((src >= 0 ? src : 2 * A - 1 - src) * PSZ);
 }
-constexpr unsigned kLutConstShift = 30;   // float32 table entries: bits 31-30 = 0 load / 1 K1 / 2 K2 / 3 M
 
 // A bytes of env `env` of an [N][A] byte array as one word per thread where A allows it
 template <int A>
@@ -119,6 +131,84 @@ __device__ __forceinline__ void tpe_store_row(void *base, int env, const unsigne
     } else {
 #pragma unroll
         for (int k = 0; k < A; ++k) q[k] = (unsigned char)v[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// float32 observation rows through TMA: the rows of the group whose templates sit in the warp's template
+// buffer (`sbase`, shared address).  Every env's block (A rows) is assembled in one of kImgRing image
+// buffers — lane l gathers pairs l, l+32, ... through the per-CTA offset table — and leaves the SM as
+// ONE bulk asynchronous copy.  (Measured alternatives, DESIGN.md §5: spreading these envs over the phases
+// of the next group's step as a software pipeline, 2 or 4 envs at a time, was slower — every
+// fence.proxy.async is also a MEMBAR that drains the step's own loads and stores.)
+// ---------------------------------------------------------------------------------------------------
+template <int A, int OBS>
+__device__ __forceinline__ void tpe_emit_group_tma(const unsigned *lut, unsigned sbase, void *obs, int g, int envs_here, int lane) {
+    using L = TpeLayout<A, OBS>;
+    static_assert(L::kImgRing == 2, "the env loop is unrolled by the ring size");
+    // src[j]: shared address, inside the template of the env being emitted, of the pair that feeds
+    // output pair lane + 32 j (the same offsets for every env)
+    unsigned src[L::kImgInstr];
+#pragma unroll
+    for (int j = 0; j < L::kImgInstr; ++j) src[j] = sbase + lut[j * 32 + lane];
+    const unsigned img0 = sbase + L::kTplBytesPerWarp;                   // image ring of this warp
+    const unsigned islot = img0 + 8u * lane;                             // this lane's pair slot of image 0
+    unsigned char *dst = static_cast<unsigned char *>(obs) + (size_t)g * 32 * L::kImgBytes;
+    auto emit_env = [&](const unsigned t_imm, const unsigned buf) {      // both compile-time after inlining
+        // the image buffer is free once the bulk copy issued kImgRing envs ago has read it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(L::kImgRing - 1) : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < L::kImgInstr; ++j) {
+            uint2 o;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(src[j] + t_imm));
+            if (j * 32 + 32 <= L::PPE || lane + j * 32 < L::PPE)
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(islot + buf + 256u * j), "r"(o.x), "r"(o.y) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy read
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(img0 + buf), "n"(L::kImgBytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        dst += L::kImgBytes;
+    };
+    int e = 0;
+    for (; e + 2 <= envs_here; e += 2) {
+        emit_env(0u, 0u);
+        emit_env((unsigned)L::TSB, (unsigned)L::kImgBytes);
+#pragma unroll
+        for (int j = 0; j < L::kImgInstr; ++j) src[j] += 2u * L::TSB;
+    }
+    if (e < envs_here) emit_env(0u, 0u);    // odd tail of a ragged last group
+}
+
+// The same rows with st.global (CCB_TPE_TMA = 0): blocks [B0, B1) of the group, a
+// block being EB envs = JB rows of 32 consecutive pairs (256 contiguous bytes per store instruction).
+template <int A, int OBS, int B0, int B1>
+__device__ __forceinline__ void tpe_emit_blocks_stg(const unsigned *lut, unsigned sbase, const unsigned char *wstage, void *obs, int g_prev,
+                                                    int envs_prev, int lane) {
+    using L = TpeLayout<A, OBS>;
+    if (g_prev < 0) return;                              // warp-uniform
+    uint2 *outp = reinterpret_cast<uint2 *>(obs) + (size_t)g_prev * 32 * L::PPE + lane;
+    if (envs_prev == 32) {
+#pragma unroll
+        for (int j = 0; j < L::JB; ++j) {
+            const unsigned a0 = sbase + lut[j * 32 + lane];
+#pragma unroll
+            for (int b = B0; b < B1; ++b) {
+                uint2 o;
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(a0 + (unsigned)(b * L::EB * L::TSB)));
+                __stcs(outp + b * L::EB * L::PPE + 32 * j, o);
+            }
+        }
+    } else if (B0 == 0) {
+        // ragged last group of a launch: plain index arithmetic, once, at most one warp per launch
+        const int npair = envs_prev * L::PPE;
+        for (int v = lane; v < npair; v += 32) {
+            const int e = v / L::PPE, r = v % L::PPE;
+            __stcs(outp + (v - lane), *reinterpret_cast<const uint2 *>(wstage + e * L::TSB + tpe_pair_offset<A, L::PSZ>(r)));
+        }
     }
 }
 
@@ -174,23 +264,21 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             // entry (j, lane) describes unit v = lane + 32 j of a block: env e = v / UPE, unit r = v % UPE of that env
             const int entry = w / L::kLutEntryWords, part = w % L::kLutEntryWords;
             const int v = (entry & 31) + 32 * (entry >> 5), e = v / L::UPE, r = v % L::UPE;
-            if (L::kPairwise) {
-                const int src = tpe_source<A>(r / L::R, r % L::R);
-                lut[w] = src >= 0 ? (unsigned)(e * L::TSB + src * L::PSZ) : ((unsigned)(-src) << kLutConstShift);
+            if (L::kTma) {
+                // entry (j, lane): pair w = lane + 32 j of ANY env (offset inside that env's template)
+                lut[w] = w < L::PPE ? tpe_pair_offset<A, L::PSZ>(w) : 0u;
+            } else if (L::kPairwise) {
+                lut[w] = (unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(r);
             } else {
                 lut[w] = ((unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(8 * r + 2 * part)) |
                          (((unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(8 * r + 2 * part + 1)) << 16);
             }
         }
-        if (OBS == CC_OBS_INT8) {   // the constant pairs of this thread's template
+        {   // the constant pairs of this thread's template
             P2 *t = reinterpret_cast<P2 *>(tpl);
             t[2 * A] = mk_pair<OT>(p.DC, p.D); t[2 * A + 1] = mk_pair<OT>(p.DL, p.DR); t[2 * A + 2] = mk_pair<OT>(-1, -1);
         }
     }
-    // float32 rows: the constant pairs as register values
-    const uint2 kc1 = make_uint2(__float_as_uint((float)p.DC), __float_as_uint((float)p.D));
-    const uint2 kc2 = make_uint2(__float_as_uint((float)p.DL), __float_as_uint((float)p.DR));
-    const uint2 kcm = make_uint2(__float_as_uint(-1.f), __float_as_uint(-1.f));
     unsigned long long *red = red_all + warp * kStCount;
     if (lane < kStCount) red[lane] = 0ull;
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.tpe_counter_next = 0u;   // the counter the NEXT launch uses
@@ -205,6 +293,11 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     // atomic counter, fetched one iteration ahead so that the round trip is hidden.  Compared with a
     // fixed stride this has no partially filled last round, and the groups in flight stay a compact,
     // ascending window of the output (profiles/probes/store_pattern_probe.cu: 6.2 -> 6.9 TB/s).
+#if CCB_TPE_STAGGER_NS > 0
+    // de-phase the warps of an SM: all warps of a launch would otherwise step their first group together,
+    // then store together, and so on (the store phase is paced by HBM and re-synchronises them)
+    if (kHasObs) __nanosleep((unsigned)((warp & 3) * CCB_TPE_STAGGER_NS));
+#endif
     int g = (int)blockIdx.x * kTpeWarps + warp;
     int g_next = 0;
     for (; g < n_groups; g = g_next) {
@@ -475,8 +568,10 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         if (kHasObs) {
             if constexpr (OBS == CC_OBS_FP32) {
 #pragma unroll
-                for (int k = 0; k < A; ++k)
-                    reinterpret_cast<float4 *>(tpl)[k] = make_float4((float)(int)(pos[k] >> 8), (float)(int)(pos[k] & 0xffu), k < p.B ? 0.f : 1.f, (float)(fl[k] & 1u));
+                for (int k = 0; k < A; ++k) {
+                    reinterpret_cast<float2 *>(tpl)[2 * k] = make_float2((float)(int)(pos[k] >> 8), (float)(int)(pos[k] & 0xffu));
+                    reinterpret_cast<float2 *>(tpl)[2 * k + 1] = make_float2(k < p.B ? 0.f : 1.f, (float)(fl[k] & 1u));
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < A; ++k)
@@ -484,33 +579,10 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             }
             __syncwarp();
             const unsigned sbase = (unsigned)__cvta_generic_to_shared(wstage);
-            if constexpr (L::kPairwise) {
-                uint2 *outp = reinterpret_cast<uint2 *>(p.obs) + (size_t)g * 32 * L::PPE + lane;
-                if (envs_here == 32) {
-#pragma unroll
-                    for (int j = 0; j < L::JB; ++j) {
-                        const unsigned d = lut[j * 32 + lane], code = d >> kLutConstShift;
-                        const unsigned a0 = sbase + d;                     // (unused when code != 0)
-                        const uint2 cv = code == 1 ? kc1 : (code == 2 ? kc2 : kcm);
-#pragma unroll
-                        for (int b = 0; b < L::NB; ++b) {
-                            uint2 o;   // constant lanes keep their register value: they make no shared-memory access
-                            asm volatile("{\n\t.reg .pred pc;\n\tsetp.ne.u32 pc, %3, 0;\n\tmov.b32 %0, %4;\n\tmov.b32 %1, %5;\n\t"
-                                         "@!pc ld.shared.v2.b32 {%0, %1}, [%2];\n\t}"
-                                         : "=&r"(o.x), "=&r"(o.y) : "r"(a0 + (unsigned)(b * L::EB * L::TSB)), "r"(code), "r"(cv.x), "r"(cv.y));
-                            __stcs(outp + b * L::EB * L::PPE + 32 * j, o);
-                        }
-                    }
-                } else {
-                    // ragged last group of a launch: plain index arithmetic, at most one warp per launch
-                    const int npair = envs_here * L::PPE;
-                    for (int v = lane; v < npair; v += 32) {
-                        const int e = v / L::PPE, r = v % L::PPE, src = tpe_source<A>(r / L::R, r % L::R);
-                        uint2 o = src == kSrcK1 ? kc1 : (src == kSrcK2 ? kc2 : kcm);
-                        if (src >= 0) o = *reinterpret_cast<const uint2 *>(wstage + e * L::TSB + src * L::PSZ);
-                        __stcs(outp + (v - lane), o);
-                    }
-                }
+            if constexpr (L::kTma) {
+                tpe_emit_group_tma<A, OBS>(lut, sbase, p.obs, g, envs_here, lane);
+            } else if constexpr (L::kPairwise) {
+                tpe_emit_blocks_stg<A, OBS, 0, L::NB>(lut, sbase, wstage, p.obs, g, envs_here, lane);
             } else {
                 uint4 *outv = reinterpret_cast<uint4 *>(p.obs) + (size_t)g * 32 * L::VPE + lane;
                 if (envs_here == 32) {
@@ -547,6 +619,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
 #endif
     }
 
+    if (L::kTma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until the copies are done
     // ---- statistics: per-warp slots in shared memory -> one atomic per slot per CTA ----------------
     {
         double rs = st_rsum;
