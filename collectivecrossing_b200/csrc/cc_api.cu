@@ -159,12 +159,16 @@ int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
     p.n_groups = (h->n_envs + 31) / 32;
     // greedy / waiting: a private lattice bitmap per thread while the lattice is small (README: 6 words)
     const bool on_device_policy = p.policy == CC_POLICY_GREEDY || p.policy == CC_POLICY_WAITING;
-    p.tpe_bm_words = (on_device_policy && p.walk_words <= ccb::kTpeMaxBitmapWords) ? p.walk_words : 0;
+    // (with TMA rows the bitmap aliases the warp's image ring: 128 bytes per word)
+    const int bm_cap = L::kTma ? (L::kImgRing * L::kImgBytes / 128 < ccb::kTpeMaxBitmapWords ? L::kImgRing * L::kImgBytes / 128 : ccb::kTpeMaxBitmapWords)
+                               : ccb::kTpeMaxBitmapWords;
+    p.tpe_bm_words = (on_device_policy && p.walk_words <= bm_cap) ? p.walk_words : 0;
     // launch k counts its groups in counter k & 1 and zeroes the other one for launch k + 1 (launches of
     // one handle are stream-ordered by contract)
     p.tpe_counter = h->tpe_counters + (h->tpe_launches & 1);
     p.tpe_counter_next = h->tpe_counters + ((h->tpe_launches + 1) & 1);
-    const int smem = L::kStageBytes + p.tpe_bm_words * ccb::kTpeThreads * 4;
+    // (with TMA rows the bitmap aliases the warp's image ring)
+    const int smem = L::kStageBytes + (L::kTma ? 0 : p.tpe_bm_words * ccb::kTpeThreads * 4);
     CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
     CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ccb::kTpeThreads, smem));

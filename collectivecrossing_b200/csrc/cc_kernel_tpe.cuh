@@ -61,7 +61,7 @@ struct TpeLayout {
     // the shared-memory work of the warps that are stepping envs (profiles/probes/lsu_coupling_probe.cu)
     static constexpr bool kTma = OBS == CC_OBS_FP32 && CCB_TPE_TMA != 0;
     static constexpr int kImgBytes = PPE * PSZ;          // 1216 B for A = 8; a multiple of 16 whenever A is even
-    static constexpr int kImgRing = 2;
+    static constexpr int kImgRing = 3;
     static constexpr int kImgInstr = (PPE + 31) / 32;    // warp instructions that cover an env's pairs
     static constexpr int kTplBytesPerWarp = kHasObs ? (32 * TSB + 15) / 16 * 16 : 0;
     static constexpr int kStageBytesPerWarp = kTplBytesPerWarp + (kTma ? kImgRing * kImgBytes : 0);
@@ -101,22 +101,19 @@ __device__ __forceinline__ unsigned tpe_pair_offset(int P) {
     return (unsigned)((src >= 0 ? src : 2 * A - 1 - src) * PSZ);
 }
 
-// A bytes of env `env` of an [N][A] byte array as one word per thread where A allows it
+// A bytes of env `env` of an [N][A] byte array: one 8-byte (A = 8) or 4-byte (A = 4) word per thread.
+// Loading (packed) and unpacking are separate so that the next group's record can be fetched early.
 template <int A>
-__device__ __forceinline__ void tpe_load_row(const void *base, int env, unsigned (&v)[A]) {
+__device__ __forceinline__ uint2 tpe_fetch_row(const void *base, int env) {
+    static_assert(A == 8 || A == 4, "rows are fetched as one aligned word");
     const unsigned char *q = static_cast<const unsigned char *>(base) + (size_t)env * A;
-    if constexpr (A == 8) {
-        const uint2 w = *reinterpret_cast<const uint2 *>(q);
+    if constexpr (A == 8) return *reinterpret_cast<const uint2 *>(q);
+    else return make_uint2(*reinterpret_cast<const unsigned *>(q), 0u);
+}
+template <int A>
+__device__ __forceinline__ void tpe_unpack_row(uint2 w, unsigned (&v)[A]) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { v[k] = (w.x >> (8 * k)) & 0xffu; v[4 + k] = (w.y >> (8 * k)) & 0xffu; }
-    } else if constexpr (A == 4) {
-        const unsigned w = *reinterpret_cast<const unsigned *>(q);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (w >> (8 * k)) & 0xffu;
-    } else {
-#pragma unroll
-        for (int k = 0; k < A; ++k) v[k] = q[k];
-    }
+    for (int k = 0; k < A; ++k) v[k] = ((k < 4 ? w.x : w.y) >> (8 * (k & 3))) & 0xffu;
 }
 template <int A>
 __device__ __forceinline__ void tpe_store_row(void *base, int env, const unsigned (&v)[A]) {
@@ -134,6 +131,8 @@ __device__ __forceinline__ void tpe_store_row(void *base, int env, const unsigne
     }
 }
 
+struct TpeConstPairs { uint2 k1, k2, m; };   // (DC, D), (DL, DR), (-1, -1) as float32 bit patterns
+
 // ---------------------------------------------------------------------------------------------------
 // float32 observation rows through TMA: the rows of the group whose templates sit in the warp's template
 // buffer (`sbase`, shared address).  Every env's block (A rows) is assembled in one of kImgRing image
@@ -143,44 +142,62 @@ __device__ __forceinline__ void tpe_store_row(void *base, int env, const unsigne
 // fence.proxy.async is also a MEMBAR that drains the step's own loads and stores.)
 // ---------------------------------------------------------------------------------------------------
 template <int A, int OBS>
-__device__ __forceinline__ void tpe_emit_group_tma(const unsigned *lut, unsigned sbase, void *obs, int g, int envs_here, int lane) {
+__device__ __forceinline__ void tpe_emit_group_tma(const unsigned *lut, unsigned sbase, void *obs, int g, int envs_here, int lane, const TpeConstPairs &kc) {
     using L = TpeLayout<A, OBS>;
-    static_assert(L::kImgRing == 2, "the env loop is unrolled by the ring size");
-    // src[j]: shared address, inside the template of the env being emitted, of the pair that feeds
-    // output pair lane + 32 j (the same offsets for every env)
+    static_assert(L::kImgRing == 3, "the env loop is unrolled by the ring size");
+    // src[j]: shared address, inside the template of the env being emitted, of the pair that feeds output
+    // pair lane + 32 j (the same offsets for every env) — or 0xFFFFFFFF when that pair is one of the constants
+    // K1, K2, M: such a lane keeps the constant in val[j] for the whole group and makes NO shared-memory
+    // access (the predicated load below), which is what keeps the gather free of bank conflicts: the other
+    // lanes of a half-warp read consecutive template pairs.
     unsigned src[L::kImgInstr];
+    unsigned long long val[L::kImgInstr];
 #pragma unroll
-    for (int j = 0; j < L::kImgInstr; ++j) src[j] = sbase + lut[j * 32 + lane];
+    for (int j = 0; j < L::kImgInstr; ++j) {
+        const unsigned d = lut[j * 32 + lane];
+        src[j] = (d >> 31) ? 0xFFFFFFFFu : sbase + d;
+        const uint2 c = (d & 3u) == 1u ? kc.k1 : ((d & 3u) == 2u ? kc.k2 : kc.m);
+        val[j] = (unsigned long long)c.x | ((unsigned long long)c.y << 32);
+    }
     const unsigned img0 = sbase + L::kTplBytesPerWarp;                   // image ring of this warp
     const unsigned islot = img0 + 8u * lane;                             // this lane's pair slot of image 0
     unsigned char *dst = static_cast<unsigned char *>(obs) + (size_t)g * 32 * L::kImgBytes;
+    unsigned long long l2_evict_first;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_evict_first));
     auto emit_env = [&](const unsigned t_imm, const unsigned buf) {      // both compile-time after inlining
         // the image buffer is free once the bulk copy issued kImgRing envs ago has read it
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(L::kImgRing - 1) : "memory");
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < L::kImgInstr; ++j) {
-            uint2 o;
-            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(src[j] + t_imm));
+            asm volatile("{\n\t.reg .pred pl;\n\tsetp.ne.u32 pl, %1, 0xFFFFFFFF;\n\t@pl ld.shared.b64 %0, [%2];\n\t}"
+                         : "+l"(val[j]) : "r"(src[j]), "r"(src[j] + t_imm));
             if (j * 32 + 32 <= L::PPE || lane + j * 32 < L::PPE)
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(islot + buf + 256u * j), "r"(o.x), "r"(o.y) : "memory");
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(islot + buf + 256u * j), "l"(val[j]) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy read
         __syncwarp();
         if (lane == 0) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(img0 + buf), "n"(L::kImgBytes) : "memory");
+            // (evict_first: the rows are written once and not read by this kernel; they must not push the state out of L2)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         ::"l"(dst), "r"(img0 + buf), "n"(L::kImgBytes), "l"(l2_evict_first) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         dst += L::kImgBytes;
     };
+    // a group starts on buffer 0 whatever the previous group ended on: all earlier copies must have been read
+    // (they were issued a whole step ago; this does not wait in practice)
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     int e = 0;
-    for (; e + 2 <= envs_here; e += 2) {
+    for (; e + 3 <= envs_here; e += 3) {
         emit_env(0u, 0u);
         emit_env((unsigned)L::TSB, (unsigned)L::kImgBytes);
+        emit_env(2u * L::TSB, 2u * L::kImgBytes);
 #pragma unroll
-        for (int j = 0; j < L::kImgInstr; ++j) src[j] += 2u * L::TSB;
+        for (int j = 0; j < L::kImgInstr; ++j) src[j] = src[j] == 0xFFFFFFFFu ? src[j] : src[j] + 3u * L::TSB;
     }
-    if (e < envs_here) emit_env(0u, 0u);    // odd tail of a ragged last group
+    if (e < envs_here) emit_env(0u, 0u);                                              // 32 = 10 x 3 + 2
+    if (e + 1 < envs_here) emit_env((unsigned)L::TSB, (unsigned)L::kImgBytes);
 }
 
 // The same rows with st.global (CCB_TPE_TMA = 0): blocks [B0, B1) of the group, a
@@ -226,13 +243,18 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PW = p.W + 3, PH = p.H + 3;  // lattice padded by one ring: x in [-1, W+1] -> column x+1
     __shared__ unsigned xt[kMaxPad], yt[2 * kMaxPad], walk[kMaxWalkWords];
-    __shared__ float rtab[2 * kRtabSize];
+    __shared__ float rtab[kRtabSize];   // value for a boarding agent; exiting agents of the default reward get the negative
     __shared__ uint8_t act_tab[kPolicyRows * 16];
     __shared__ unsigned long long red_all[kTpeWarps * kStCount];
     __shared__ __align__(16) unsigned lut[L::kLutWords];   // emission table, see TpeLayout
     unsigned char *wstage = smem + warp * L::kStageBytesPerWarp;   // this warp's 32 templates
     unsigned char *tpl = wstage + lane * L::TSB;                    // this thread's env
-    unsigned *bm = reinterpret_cast<unsigned *>(smem + L::kStageBytes) + threadIdx.x;   // private lattice bitmap (policies)
+    // private lattice bitmap of the policies: word w of this thread at bm[w * kBmStride].  With TMA rows it
+    // lives in the warp's image ring, which is idle while the warp steps its envs (kBmStride = 32 lanes);
+    // otherwise in its own region behind the templates (kBmStride = threads of the CTA).
+    constexpr int kBmStride = L::kTma ? 32 : kTpeThreads;
+    unsigned *bm = L::kTma ? reinterpret_cast<unsigned *>(wstage + L::kTplBytesPerWarp) + lane
+                           : reinterpret_cast<unsigned *>(smem + L::kStageBytes) + threadIdx.x;
 
     // ---- once per CTA: tables (same contents as cc_kernels.cuh) -------------------------------------
     for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
@@ -242,10 +264,9 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         // distance rewards: float((double)(-+d) * f), the reference's float64 product rounded once
         // (rewards.py:85,99,127); constants for binary / constant_negative (rewards.py:152-159,179-182)
         const double f = p.reward_kind == CC_REWARD_DEFAULT ? p.rp[3] : p.rp[0];
-        for (int i = threadIdx.x; i < 2 * kRtabSize; i += blockDim.x) {
-            const int type = i / kRtabSize, d = i % kRtabSize - kYBias;
-            const bool negate = type == 0 || p.reward_kind == CC_REWARD_SIMPLE_DISTANCE;
-            float v = (float)((double)(negate ? -d : d) * f);
+        for (int i = threadIdx.x; i < kRtabSize; i += blockDim.x) {
+            const int d = i - kYBias;
+            float v = (float)((double)(-d) * f);      // boarding / simple distance; exiting (default): float((double)d * f) = 0 - v exactly
             if (p.reward_kind == CC_REWARD_BINARY) v = p.rpf[1];
             if (p.reward_kind == CC_REWARD_CONSTANT_NEGATIVE) v = p.rpf[0];
             rtab[i] = v;
@@ -266,7 +287,8 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             const int v = (entry & 31) + 32 * (entry >> 5), e = v / L::UPE, r = v % L::UPE;
             if (L::kTma) {
                 // entry (j, lane): pair w = lane + 32 j of ANY env (offset inside that env's template)
-                lut[w] = w < L::PPE ? tpe_pair_offset<A, L::PSZ>(w) : 0u;
+                const int src = w < L::PPE ? tpe_source<A>(w / L::R, w % L::R) : kSrcM;
+                lut[w] = src >= 0 ? (unsigned)(src * L::PSZ) : (0x80000000u | (unsigned)(-src));
             } else if (L::kPairwise) {
                 lut[w] = (unsigned)(e * L::TSB) + tpe_pair_offset<A, L::PSZ>(r);
             } else {
@@ -279,6 +301,9 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             t[2 * A] = mk_pair<OT>(p.DC, p.D); t[2 * A + 1] = mk_pair<OT>(p.DL, p.DR); t[2 * A + 2] = mk_pair<OT>(-1, -1);
         }
     }
+    const TpeConstPairs kc = {make_uint2(__float_as_uint((float)p.DC), __float_as_uint((float)p.D)),
+                              make_uint2(__float_as_uint((float)p.DL), __float_as_uint((float)p.DR)),
+                              make_uint2(__float_as_uint(-1.f), __float_as_uint(-1.f))};
     unsigned long long *red = red_all + warp * kStCount;
     if (lane < kStCount) red[lane] = 0ull;
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.tpe_counter_next = 0u;   // the counter the NEXT launch uses
@@ -298,9 +323,24 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     // then store together, and so on (the store phase is paced by HBM and re-synchronises them)
     if (kHasObs) __nanosleep((unsigned)((warp & 3) * CCB_TPE_STAGGER_NS));
 #endif
+    // The record of a group: one word per byte row, step counter, return.  (Fetching it one group ahead,
+    // before the previous group's rows are streamed out, was measured: no gain, 10 more live registers.)
+    struct Record { uint2 x, y, fl, act; int step; float ep_ret; };
+    auto fetch = [&](int gg, Record &r) {
+        const long long n = (long long)gg * 32 + lane;
+        const int nl = n < p.n_envs ? (int)n : (int)p.n_envs - 1;    // threads beyond the end re-read the last env (never stored)
+        r.x = tpe_fetch_row<A>(p.x, nl);
+        r.y = tpe_fetch_row<A>(p.y, nl);
+        r.fl = tpe_fetch_row<A>(p.flags, nl);
+        r.act = p.policy == CC_POLICY_EXTERNAL ? tpe_fetch_row<A>(p.actions, nl) : make_uint2(0u, 0u);
+        r.step = p.step[nl];
+        r.ep_ret = p.ep_ret[nl];
+    };
     int g = (int)blockIdx.x * kTpeWarps + warp;
     int g_next = 0;
+    Record rec;
     for (; g < n_groups; g = g_next) {
+        fetch(g, rec);
 #if CCB_TPE_DYNAMIC
         if (lane == 0) g_next = total_warps + (int)atomicAdd(p.tpe_counter, 1u);
 #else
@@ -309,21 +349,20 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         const int n = g * 32 + lane;
         const int envs_here = (int)min(32ll, p.n_envs - (long long)g * 32);
         const bool env_ok = lane < envs_here;                 // false only in the ragged last group
-        const int nl = env_ok ? n : (int)p.n_envs - 1;        // threads beyond the end re-read the last env (never stored)
         const unsigned long long genv = p.genv_offset + (unsigned long long)n;
 
-        // ---- the env's record -------------------------------------------------------------------
+        // ---- the env's record -------------------------------------------------------------------------
         unsigned px[A], py[A], fl[A], action[A];
-        tpe_load_row<A>(p.x, nl, px);
-        tpe_load_row<A>(p.y, nl, py);
-        tpe_load_row<A>(p.flags, nl, fl);
-        if (p.policy == CC_POLICY_EXTERNAL) tpe_load_row<A>(p.actions, nl, action);
+        tpe_unpack_row<A>(rec.x, px);
+        tpe_unpack_row<A>(rec.y, py);
+        tpe_unpack_row<A>(rec.fl, fl);
+        if (p.policy == CC_POLICY_EXTERNAL) tpe_unpack_row<A>(rec.act, action);
         else {
 #pragma unroll
             for (int k = 0; k < A; ++k) action[k] = CC_ACT_WAIT;
         }
-        int step = p.step[nl];
-        float ep_ret = p.ep_ret[nl];
+        int step = rec.step;
+        float ep_ret = rec.ep_ret;
         unsigned pos[A];
 #pragma unroll
         for (int k = 0; k < A; ++k) { pos[k] = (px[k] << 8) | py[k]; fl[k] = env_ok ? fl[k] : 0u; }
@@ -375,16 +414,20 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             unsigned vmask[A];
             if (p.tpe_bm_words > 0) {
                 // small lattice: the thread keeps a private bitmap "wall or occupied" of the padded
-                // lattice in shared memory (word w at bm[w * kTpeThreads]: a thread only ever touches
+                // lattice in shared memory (word w at bm[w * kBmStride]: a thread only ever touches
                 // its own bank), so a move is valid iff ONE bit is clear
-                for (int w = 0; w < p.tpe_bm_words; ++w) bm[w * kTpeThreads] = ~walk[w];
+                if constexpr (L::kTma) {   // the ring must have been read by the previous group's copies (issued long ago)
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                }
+                for (int w = 0; w < p.tpe_bm_words; ++w) bm[w * kBmStride] = ~walk[w];
 #pragma unroll
                 for (int k = 0; k < A; ++k)
-                    if (fl[k] & CC_F_ACTIVE) bm[(cell[k] >> 5) * kTpeThreads] |= 1u << (cell[k] & 31);
+                    if (fl[k] & CC_F_ACTIVE) bm[(cell[k] >> 5) * kBmStride] |= 1u << (cell[k] & 31);
 #pragma unroll
                 for (int k = 0; k < A; ++k) {
                     const int c = cell[k];
-                    auto blocked = [&](int idx) { return (bm[(idx >> 5) * kTpeThreads] >> (idx & 31)) & 1u; };
+                    auto blocked = [&](int idx) { return (bm[(idx >> 5) * kBmStride] >> (idx & 31)) & 1u; };
                     vmask[k] = (blocked(c + 1) | (blocked(c + PW) << 1) | (blocked(c - 1) << 2) | (blocked(c - PW) << 3)) ^ 15u;
                 }
             } else {
@@ -453,7 +496,8 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         for (int k = 0; k < A; ++k) {
             // one path for the four reward functions, see cc_kernels.cuh (rewards.py:65-66,78-99,127,152-159,179-182)
             const unsigned f = geo_f[k];
-            float r = rtab[(k < p.B ? 0 : kRtabSize) + (int)((geo_u[k] >> 8) & 0x1ffu)];
+            float r = rtab[(int)((geo_u[k] >> 8) & 0x1ffu)];
+            if (k >= p.B && p.reward_kind == CC_REWARD_DEFAULT) r = 0.f - r;   // rewards.py:95-99: the exiting term is positive (sic)
             const bool boarding = k < p.B;
             const float special = boarding ? ((f & 2u) ? p.rpf[1] : p.rpf[2]) : p.rpf[2];
             const unsigned in_special = boarding ? (f & 3u) : ((f & 1u) ^ 1u);
@@ -564,6 +608,10 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             p.env_flags[n] = (uint8_t)eflags;
         }
 
+#if CCB_TPE_DYNAMIC
+        g_next = __shfl_sync(kFull, g_next, 0);
+#endif
+
         // ---- observations.py:43-94 from the post-step (post-reset) state --------------------------
         if (kHasObs) {
             if constexpr (OBS == CC_OBS_FP32) {
@@ -580,7 +628,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             __syncwarp();
             const unsigned sbase = (unsigned)__cvta_generic_to_shared(wstage);
             if constexpr (L::kTma) {
-                tpe_emit_group_tma<A, OBS>(lut, sbase, p.obs, g, envs_here, lane);
+                tpe_emit_group_tma<A, OBS>(lut, sbase, p.obs, g, envs_here, lane, kc);
             } else if constexpr (L::kPairwise) {
                 tpe_emit_blocks_stg<A, OBS, 0, L::NB>(lut, sbase, wstage, p.obs, g, envs_here, lane);
             } else {
@@ -614,9 +662,6 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             }
             __syncwarp();
         }
-#if CCB_TPE_DYNAMIC
-        g_next = __shfl_sync(kFull, g_next, 0);
-#endif
     }
 
     if (L::kTma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until the copies are done
