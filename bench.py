@@ -315,8 +315,9 @@ def run_ours(args):
             traffic = json.loads(tp.read_text()).get(f"{args.obs_dtype}_{args.policy}_{n}")
         except Exception:
             traffic = None
+    kernel_name = ("ccb::cc_step_tpe_kernel<8,%s>" if env.last_kernel == "threads" else "ccb::cc_kernel<8,1,%s,step>") % {"float32": 4, "int8": 1, "none": 0}[args.obs_dtype]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "ccb::cc_kernel<8,1,%s,step>" % {"float32": 4, "int8": 1, "none": 0}[args.obs_dtype],
+                "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_env_step": env.algorithmic_bytes_per_env_step(),
                 "formula": "12A+17+s_obs*A*(6+4A), A=8 (SURVEY.md 8d)"}
 
@@ -377,21 +378,40 @@ def run_ours(args):
 
 
 def secondary(args, torch, dist, cfg):
-    """Secondary single-GPU measurements (reported under "extras", never as `value`)."""
+    """Secondary single-GPU measurements (reported under "extras", never as `value`): the other obs
+    dtypes / policies of the headline config, the lane-group mapping, and the shapes of BASELINE
+    configs 3, 4 and 5 on one GPU."""
+    from cases import large_config, readme_config
+
     from collectivecrossing_b200 import BatchedCollectiveCrossing
 
     out = {}
     dev = torch.device("cuda", torch.cuda.current_device())
-    for tag, n, obs, pol in (("cfg2_65536_envs_fp32_greedy", 65536, "float32", "greedy"), ("1M_envs_int8_greedy", 1 << 20, "int8", "greedy"),
-                             ("1M_envs_noobs_greedy", 1 << 20, "none", "greedy"), ("1M_envs_fp32_waiting", 1 << 20, "float32", "waiting"),
-                             ("1M_envs_fp32_random", 1 << 20, "float32", "random")):
-        env = BatchedCollectiveCrossing(cfg, n, dev, seed=1, obs_dtype=obs, auto_reset=True)
+    M = 1 << 20
+    runs = (
+        # tag, config, envs, obs dtype, policy, kernel, timed steps
+        ("cfg2_65536_envs_fp32_greedy", cfg, 65536, "float32", "greedy", "auto", 50),
+        ("1M_envs_int8_greedy", cfg, M, "int8", "greedy", "auto", 50),
+        ("1M_envs_noobs_greedy", cfg, M, "none", "greedy", "auto", 50),
+        ("1M_envs_fp32_waiting", cfg, M, "float32", "waiting", "auto", 50),
+        ("1M_envs_fp32_random", cfg, M, "float32", "random", "auto", 50),
+        ("1M_envs_fp32_greedy_lane_group_kernel", cfg, M, "float32", "greedy", "lanes", 50),
+        ("cfg3_64x32_64agents_simple_distance_all_1M_envs_int8_random", large_config(512), M, "int8", "random", "auto", 5),
+        ("cfg4_binary_individual_4M_envs_fp32_random", readme_config("binary", "individual", 100, goal_reward=1.0, no_goal_reward=0.0), 4 * M, "float32", "random", "auto", 10),
+        ("cfg4_constant_negative_individual_4M_envs_fp32_random", readme_config("constant_negative", "individual", 100, step_penalty=-1.0), 4 * M, "float32", "random", "auto", 10),
+        ("cfg5_shard_2M_envs_fp32_waiting", cfg, 2 * M, "float32", "waiting", "auto", 20),
+    )
+    for tag, c, n, obs, pol, kern, steps in runs:
+        env = BatchedCollectiveCrossing(c, n, dev, seed=1, obs_dtype=obs, auto_reset=True, kernel=kern)
         env.reset()
-        for _ in range(10):
+        for _ in range(5):
             env.step(policy=pol)
-        ms = time_steps(env, torch, dist, args, 50, pol, 1)
+        ms = time_steps(env, torch, dist, args, steps, pol, 1)
+        env.check_error()
         b = env.algorithmic_bytes_per_env_step() * n
-        out[tag] = {"agent_steps_per_sec": n * 8 * 50 / (ms * 1e-3), "ms_per_step": ms / 50, "algorithmic_GBps": b / (ms / 50 * 1e-3) / 1e9}
+        a = env.num_agents
+        out[tag] = {"agent_steps_per_sec": n * a * steps / (ms * 1e-3), "ms_per_step": ms / steps, "algorithmic_GBps": b / (ms / steps * 1e-3) / 1e9,
+                    "kernel": env.last_kernel, "agents_per_env": a, "envs": n}
         env.close()
         del env
         torch.cuda.empty_cache()
