@@ -20,6 +20,7 @@ _LAZY = {
     "StepOutput": ("batched", "StepOutput"),
     "CollectiveCrossingEnv": ("env", "CollectiveCrossingEnv"),
     "ShardedCollectiveCrossing": ("distributed", "ShardedCollectiveCrossing"),
+    "VectorCollectiveCrossing": ("vector_env", "VectorCollectiveCrossing"),
 }
 
 

@@ -272,13 +272,11 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             rtab[i] = v;
         }
     }
-    for (int w = threadIdx.x; w < p.walk_words; w += blockDim.x) {   // collectivecrossing.py:509-534 as a bitmap
-        unsigned bits = 0;
-        for (int b = 0; b < 32; ++b) {
-            const int idx = w * 32 + b, yy = idx / PW - 1, xx = idx - (yy + 1) * PW - 1;
-            bits |= valid_position(p, xx, yy) ? (1u << b) : 0u;
-        }
-        walk[w] = bits;
+    // collectivecrossing.py:509-534 as a bitmap of the padded lattice: a warp builds one word per ballot
+    for (int w = warp; w < p.walk_words; w += kTpeWarps) {
+        const int idx = w * 32 + lane, yy = idx / PW - 1, xx = idx - (yy + 1) * PW - 1;
+        const unsigned bits = __ballot_sync(kFull, valid_position(p, xx, yy));
+        if (lane == 0) walk[w] = bits;
     }
     if (kHasObs) {
         for (int w = threadIdx.x; w < L::kLutWords; w += blockDim.x) {

@@ -7,8 +7,8 @@ come back exactly as the reference computes them), ``reset(seed=...)`` runs the 
 PCG64 placement kernel.  What stays on the host is bookkeeping: the ``_agents`` records tests and
 policies read or overwrite (state injection), dict assembly, argument validation.
 
-Not provided: rendering (``render`` raises ``NotImplementedError``; matplotlib drawing is outside
-the hot path).  Known divergence: an invalid action raises ``ValueError`` BEFORE anything moves,
+Rendering: ``render()`` returns an ``rgb_array`` from a numpy rasteriser (``rendering.py``); the
+interactive matplotlib ``human`` mode is not provided.  Known divergence: an invalid action raises ``ValueError`` BEFORE anything moves,
 while the reference raises midway through its move loop (collectivecrossing.py:197-202) leaving
 earlier agents moved and the step counter bumped.
 """
@@ -110,8 +110,15 @@ class CollectiveCrossingEnv(_Base):
     def close(self) -> None:
         self._dev.close()
 
-    def render(self, mode: str = "rgb_array"):
-        raise NotImplementedError("rendering is outside the B200 hot path; use the reference's rendering module")
+    def render(self, mode: str | None = None):
+        """``rgb_array`` image of the current host view (numpy rasteriser, ``rendering.py``); the
+        reference's interactive ``human`` mode needs matplotlib and is not provided."""
+        mode = mode or getattr(self._config, "render_mode", None) or "rgb_array"
+        if mode != "rgb_array":
+            raise NotImplementedError("only render_mode='rgb_array' is available (no matplotlib in this stack)")
+        from .rendering import render_env
+
+        return render_env(self)
 
     # ---- construction helpers ----------------------------------------------------------------------
     def _create_dummy_agents(self) -> dict[str, Agent]:
