@@ -76,6 +76,7 @@ EXPORTS = {
     "cc_step": (C.c_int, [_P, C.POINTER(CCStepIO), _P]),
     "cc_step_host": (C.c_int, [_P, C.POINTER(CCStepIO)]),
     "cc_rollout": (C.c_int, [_P, C.POINTER(CCStepIO), _I32, _P]),
+    "cc_rollout_fused": (C.c_int, [_P, C.POINTER(CCStepIO), _I32, _P]),
     "cc_reset": (C.c_int, [_P, _P, _P, _I32, _P]),
     "cc_reset_seeded": (C.c_int, [_P, _P, _P, _I32, _P]),
     "cc_policy_actions": (C.c_int, [_P, _I32, _P, _P]),

@@ -250,6 +250,45 @@ class BatchedCollectiveCrossing:
         _native.check(self._lib.cc_rollout(self._h, C.byref(io), int(n_steps), self._stream()))
         return self._output()
 
+    def rollout_trajectory(self, n_steps: int, policy: Any = "greedy", actions: torch.Tensor | None = None,
+                           auto_reset: bool | None = None) -> dict:
+        """``n_steps`` steps whose outputs are all kept, time-major: ``obs [T, N, A, L]``, ``reward``,
+        ``agent_flags``, ``agent_info``, ``actions`` ``[T, N, A]``, ``env_flags [T, N]`` — the loop
+        "policy -> step -> reset on done" of the reference's rollout scripts for N envs.  With the
+        thread-per-env kernel (crews of 4 or 8) this is ONE launch that keeps each env's state in
+        registers for the T steps; results equal T calls of ``step``.  ``policy="external"`` reads
+        ``actions`` int8 ``[T, N, A]``.  The returned tensors are reused by the next call with the same T."""
+        T, n, a = int(n_steps), self.num_envs, self.num_agents
+        if T < 1:
+            raise ValueError("n_steps must be positive")
+        buf = getattr(self, "_traj", None)
+        if buf is None or buf["reward"].shape[0] != T:
+            dev = self.device
+            buf = self._traj = dict(
+                obs=None if self.obs is None else torch.zeros((T, n, a, self.obs_len), dtype=self.obs_torch_dtype, device=dev),
+                reward=torch.zeros((T, n, a), dtype=self.reward_torch_dtype, device=dev),
+                agent_flags=torch.zeros((T, n, a), dtype=torch.uint8, device=dev),
+                agent_info=None if self.agent_info is None else torch.zeros((T, n, a), dtype=torch.uint8, device=dev),
+                env_flags=torch.zeros((T, n), dtype=torch.uint8, device=dev),
+                actions=torch.zeros((T, n, a), dtype=torch.int8, device=dev))
+        io = _abi.CCStepIO()
+        code = _policy_code(policy)
+        if code == _abi.POLICIES["external"]:
+            if actions is None:
+                raise ValueError("policy='external' needs `actions` [T, N, A]")
+            io.actions = self._check_tensor(actions, torch.int8, (T, n, a), "actions").data_ptr()
+        io.order = None
+        io.actions_out = buf["actions"].data_ptr()
+        io.obs = None if buf["obs"] is None else buf["obs"].data_ptr()
+        io.reward = buf["reward"].data_ptr()
+        io.agent_flags = buf["agent_flags"].data_ptr()
+        io.agent_info = None if buf["agent_info"] is None else buf["agent_info"].data_ptr()
+        io.env_flags = buf["env_flags"].data_ptr()
+        io.obs_dtype, io.reward_dtype, io.policy = self.obs_code, self.reward_code, code
+        io.auto_reset = int(self.auto_reset if auto_reset is None else auto_reset)
+        _native.check(self._lib.cc_rollout_fused(self._h, C.byref(io), T, self._stream()))
+        return buf
+
     def policy_actions(self, policy: Any, out: torch.Tensor | None = None) -> torch.Tensor:
         """Actions of a baseline policy for the current state (``policy.get_action`` for every agent)."""
         out = self.actions_out if out is None else self._check_tensor(out, torch.int8, (self.num_envs, self.num_agents), "out")

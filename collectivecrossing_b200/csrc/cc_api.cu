@@ -165,6 +165,10 @@ int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
     p.tpe_bm_words = (on_device_policy && p.walk_words <= bm_cap) ? p.walk_words : 0;
     // launch k counts its groups in counter k & 1 and zeroes the other one for launch k + 1 (launches of
     // one handle are stream-ordered by contract)
+    if (p.n_steps < 1) p.n_steps = 1;
+    p.slice_agents = (long long)h->n_envs * h->A;
+    p.slice_envs = h->n_envs;
+    p.slice_obs_bytes = OBS == CC_OBS_NONE ? 0 : (long long)h->n_envs * h->A * (6 + 4 * h->A) * (long long)OBS;
     p.tpe_counter = h->tpe_counters + (h->tpe_launches & 1);
     p.tpe_counter_next = h->tpe_counters + ((h->tpe_launches + 1) & 1);
     // (with TMA rows the bitmap aliases the warp's image ring)
@@ -222,19 +226,24 @@ int check_io(const cc_handle *h, const cc_step_io *io) {
     return CC_OK;
 }
 
-int step_on(cc_handle *h, const cc_step_io *io, cudaStream_t s) {
+// n_steps > 1: one fused launch of the thread-per-env kernel; the caller has checked eligibility and that
+// every output buffer of `io` is time-major [n_steps][...]
+int step_on(cc_handle *h, const cc_step_io *io, cudaStream_t s, int n_steps = 1, long long obs_env_offset = 0) {
     KParams p;
     fill_params(h, p, io->obs_dtype, io->policy == CC_POLICY_GREEDY || io->policy == CC_POLICY_WAITING);
+    p.n_steps = n_steps;
+    p.obs_env_offset = obs_env_offset;
     p.actions = io->actions; p.order = io->order; p.actions_out = io->actions_out;
     p.obs = io->obs; p.reward = io->reward; p.agent_flags = io->agent_flags; p.agent_info = io->agent_info; p.env_flags = io->env_flags;
     p.policy = io->policy; p.auto_reset = io->auto_reset != 0; p.reward_f64 = io->reward_dtype == CC_REWARD_F64;
-    const bool can_tpe = tpe_eligible(h, io);
+    const bool can_tpe = obs_env_offset == 0 && tpe_eligible(h, io);
     if (h->variant == CC_KERNEL_THREADS && !can_tpe)
         return fail(CC_ERR_UNSUPPORTED, "CC_KERNEL_THREADS was requested but this step is not eligible (needs 4 or 8 agents, agent order, "
                                         "float32 rewards, rows aligned to the crew size)");
     const bool use_tpe = can_tpe && h->variant != CC_KERNEL_LANES;
     int rc = use_tpe ? launch_tpe(h, p, io->obs_dtype, s) : launch<ccb::kModeStep>(h, p, io->obs_dtype, s);
-    if (rc == CC_OK) { h->t += 1; h->last_variant = use_tpe ? CC_KERNEL_THREADS : CC_KERNEL_LANES; }
+    if (n_steps > 1 && !use_tpe) return fail(CC_ERR_UNSUPPORTED, "fused multi-step launches need the thread-per-env kernel");
+    if (rc == CC_OK) { h->t += (uint64_t)n_steps; h->last_variant = use_tpe ? CC_KERNEL_THREADS : CC_KERNEL_LANES; }
     return rc;
 }
 
@@ -359,6 +368,32 @@ int cc_rollout(cc_handle *h, const cc_step_io *io, int32_t n_steps, void *stream
     DeviceGuard guard(h->device);
     for (int i = 0; i < n_steps; ++i) {
         rc = step_on(h, io, static_cast<cudaStream_t>(stream));
+        if (rc != CC_OK) return rc;
+    }
+    return CC_OK;
+}
+
+int cc_rollout_fused(cc_handle *h, const cc_step_io *io, int32_t n_steps, void *stream) {
+    int rc = check_io(h, io);
+    if (rc != CC_OK) return rc;
+    if (n_steps < 1) return fail(CC_ERR_INVALID_ARG, "n_steps must be positive");
+    if (io->order) return fail(CC_ERR_INVALID_ARG, "cc_rollout_fused moves agents in agent order (io->order must be NULL)");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (tpe_eligible(h, io) && h->variant != CC_KERNEL_LANES) return step_on(h, io, s, n_steps);   // state stays in registers
+    if (h->variant == CC_KERNEL_THREADS) return fail(CC_ERR_UNSUPPORTED, "CC_KERNEL_THREADS was requested but this rollout is not eligible");
+    // any other crew / dtype: one launch per step into the time slices
+    const size_t na = (size_t)h->n_envs * h->A, n = (size_t)h->n_envs;
+    for (int t = 0; t < n_steps; ++t) {
+        cc_step_io d = *io;
+        if (io->actions) d.actions = io->actions + t * na;
+        if (io->actions_out) d.actions_out = io->actions_out + t * na;
+        // (the observation slice is addressed through an env offset: t * obs_b need not be 16-byte aligned)
+        d.reward = static_cast<char *>(io->reward) + t * na * (size_t)io->reward_dtype;
+        d.agent_flags = io->agent_flags + t * na;
+        if (io->agent_info) d.agent_info = io->agent_info + t * na;
+        d.env_flags = io->env_flags + t * n;
+        rc = step_on(h, &d, s, 1, (long long)t * h->n_envs);
         if (rc != CC_OK) return rc;
     }
     return CC_OK;

@@ -323,14 +323,13 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
 #endif
     // The record of a group: one word per byte row, step counter, return.  (Fetching it one group ahead,
     // before the previous group's rows are streamed out, was measured: no gain, 10 more live registers.)
-    struct Record { uint2 x, y, fl, act; int step; float ep_ret; };
+    struct Record { uint2 x, y, fl; int step; float ep_ret; };
     auto fetch = [&](int gg, Record &r) {
         const long long n = (long long)gg * 32 + lane;
         const int nl = n < p.n_envs ? (int)n : (int)p.n_envs - 1;    // threads beyond the end re-read the last env (never stored)
         r.x = tpe_fetch_row<A>(p.x, nl);
         r.y = tpe_fetch_row<A>(p.y, nl);
         r.fl = tpe_fetch_row<A>(p.flags, nl);
-        r.act = p.policy == CC_POLICY_EXTERNAL ? tpe_fetch_row<A>(p.actions, nl) : make_uint2(0u, 0u);
         r.step = p.step[nl];
         r.ep_ret = p.ep_ret[nl];
     };
@@ -349,21 +348,27 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         const bool env_ok = lane < envs_here;                 // false only in the ragged last group
         const unsigned long long genv = p.genv_offset + (unsigned long long)n;
 
-        // ---- the env's record -------------------------------------------------------------------------
-        unsigned px[A], py[A], fl[A], action[A];
-        tpe_unpack_row<A>(rec.x, px);
-        tpe_unpack_row<A>(rec.y, py);
-        tpe_unpack_row<A>(rec.fl, fl);
-        if (p.policy == CC_POLICY_EXTERNAL) tpe_unpack_row<A>(rec.act, action);
+        // ---- the env's record: in registers for all the steps this launch takes (cc_rollout_fused: n_steps > 1) ----
+        unsigned pos[A], fl[A];
+        {
+            unsigned px[A], py[A];
+            tpe_unpack_row<A>(rec.x, px);
+            tpe_unpack_row<A>(rec.y, py);
+            tpe_unpack_row<A>(rec.fl, fl);
+#pragma unroll
+            for (int k = 0; k < A; ++k) { pos[k] = (px[k] << 8) | py[k]; fl[k] = env_ok ? fl[k] : 0u; }
+        }
+        int step = rec.step;
+        float ep_ret = rec.ep_ret;
+      for (int tt = 0; tt < p.n_steps; ++tt) {   // (body indented as one step: time slice tt of every output)
+        const size_t slice_a = (size_t)tt * (size_t)p.slice_agents;   // offset of slice tt in a per-agent array (elements)
+        const unsigned t_rng = p.t + (unsigned)tt;                     // RNG counter word of this step
+        unsigned action[A];
+        if (p.policy == CC_POLICY_EXTERNAL) tpe_unpack_row<A>(tpe_fetch_row<A>(p.actions + slice_a, env_ok ? n : (int)p.n_envs - 1), action);
         else {
 #pragma unroll
             for (int k = 0; k < A; ++k) action[k] = CC_ACT_WAIT;
         }
-        int step = rec.step;
-        float ep_ret = rec.ep_ret;
-        unsigned pos[A];
-#pragma unroll
-        for (int k = 0; k < A; ++k) { pos[k] = (px[k] << 8) | py[k]; fl[k] = env_ok ? fl[k] : 0u; }
 
         int cell[A];
         unsigned geo_u[A], geo_f[A];
@@ -394,7 +399,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         if (p.policy == CC_POLICY_RANDOM) {
 #pragma unroll
             for (int k = 0; k < A; ++k) {
-                action[k] = (unsigned)bounded(draw(p, genv, kStreamAction, (unsigned)k).v0, 5);
+                action[k] = (unsigned)bounded(draw_at(p, t_rng, genv, kStreamAction, (unsigned)k).v0, 5);
                 lookup(k);
             }
         } else if (p.policy != CC_POLICY_EXTERNAL) {
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
 #pragma unroll
             for (int k = 0; k < A; ++k) lookup(k);
         }
-        if (p.actions_out && env_ok) tpe_store_row<A>(p.actions_out, n, action);
+        if (p.actions_out && env_ok) tpe_store_row<A>(p.actions_out + slice_a, n, action);
 
         // ---- collectivecrossing.py:188 ---------------------------------------------------------------
         step += 1;
@@ -532,7 +537,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
 
         // ---- outputs of the finished step ----------------------------------------------------------
         if (env_ok) {
-            float *rw = reinterpret_cast<float *>(p.reward) + (size_t)n * A;
+            float *rw = reinterpret_cast<float *>(p.reward) + slice_a + (size_t)n * A;
             if constexpr (A % 4 == 0) {
 #pragma unroll
                 for (int k = 0; k < A; k += 4) *reinterpret_cast<float4 *>(rw + k) = make_float4(rew[k], rew[k + 1], rew[k + 2], rew[k + 3]);
@@ -540,12 +545,12 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
 #pragma unroll
                 for (int k = 0; k < A; ++k) rw[k] = rew[k];
             }
-            tpe_store_row<A>(p.agent_flags, n, oflag);
+            tpe_store_row<A>(p.agent_flags + slice_a, n, oflag);
             if (p.agent_info) {
                 unsigned info[A];
 #pragma unroll
                 for (int k = 0; k < A; ++k) info[k] = (geo_f[k] & 0xBu) | ((fl[k] & 1u) << 2);   // :248-254
-                tpe_store_row<A>(p.agent_info, n, info);
+                tpe_store_row<A>(p.agent_info + slice_a, n, info);
             }
             st_rsum += (double)rsum;
         }
@@ -575,7 +580,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
                 unsigned cand = 0;
                 bool ok = false;
                 for (int attempt = 0; attempt < kResetAttemptCap && !ok; ++attempt) {
-                    const U4 r = draw(p, genv, kStreamReset, ((unsigned)i << 16) | (unsigned)attempt);
+                    const U4 r = draw_at(p, t_rng, genv, kStreamReset, ((unsigned)i << 16) | (unsigned)attempt);
                     int cx, cy;
                     if (i < p.B) {                                  // :103-117
                         cx = bounded(r.v0, p.W); cy = bounded(r.v1, p.D);
@@ -594,21 +599,9 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             }
         }
 
-        // ---- write back the persistent state ----------------------------------------------------
-        if (env_ok) {
+        if (env_ok) p.env_flags[(size_t)tt * (size_t)p.slice_envs + n] = (uint8_t)eflags;
 #pragma unroll
-            for (int k = 0; k < A; ++k) { px[k] = pos[k] >> 8; py[k] = pos[k] & 0xffu; fl[k] &= 7u; }
-            tpe_store_row<A>(p.x, n, px);
-            tpe_store_row<A>(p.y, n, py);
-            tpe_store_row<A>(p.flags, n, fl);
-            p.step[n] = step;
-            p.ep_ret[n] = ep_ret;
-            p.env_flags[n] = (uint8_t)eflags;
-        }
-
-#if CCB_TPE_DYNAMIC
-        g_next = __shfl_sync(kFull, g_next, 0);
-#endif
+        for (int k = 0; k < A; ++k) fl[k] &= 7u;
 
         // ---- observations.py:43-94 from the post-step (post-reset) state --------------------------
         if (kHasObs) {
@@ -625,12 +618,13 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             }
             __syncwarp();
             const unsigned sbase = (unsigned)__cvta_generic_to_shared(wstage);
+            void *obs_t = static_cast<unsigned char *>(p.obs) + (size_t)tt * (size_t)p.slice_obs_bytes;
             if constexpr (L::kTma) {
-                tpe_emit_group_tma<A, OBS>(lut, sbase, p.obs, g, envs_here, lane, kc);
+                tpe_emit_group_tma<A, OBS>(lut, sbase, obs_t, g, envs_here, lane, kc);
             } else if constexpr (L::kPairwise) {
-                tpe_emit_blocks_stg<A, OBS, 0, L::NB>(lut, sbase, wstage, p.obs, g, envs_here, lane);
+                tpe_emit_blocks_stg<A, OBS, 0, L::NB>(lut, sbase, wstage, obs_t, g, envs_here, lane);
             } else {
-                uint4 *outv = reinterpret_cast<uint4 *>(p.obs) + (size_t)g * 32 * L::VPE + lane;
+                uint4 *outv = reinterpret_cast<uint4 *>(obs_t) + (size_t)g * 32 * L::VPE + lane;
                 if (envs_here == 32) {
 #pragma unroll
                     for (int j = 0; j < L::JB; ++j) {
@@ -660,6 +654,22 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             }
             __syncwarp();
         }
+      }   // steps of this launch
+
+        // ---- write back the persistent state ----------------------------------------------------
+        if (env_ok) {
+            unsigned px[A], py[A];
+#pragma unroll
+            for (int k = 0; k < A; ++k) { px[k] = pos[k] >> 8; py[k] = pos[k] & 0xffu; }
+            tpe_store_row<A>(p.x, n, px);
+            tpe_store_row<A>(p.y, n, py);
+            tpe_store_row<A>(p.flags, n, fl);
+            p.step[n] = step;
+            p.ep_ret[n] = ep_ret;
+        }
+#if CCB_TPE_DYNAMIC
+        g_next = __shfl_sync(kFull, g_next, 0);
+#endif
     }
 
     if (L::kTma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until the copies are done
@@ -684,7 +694,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             for (int w = 0; w < kTpeWarps; ++w) v += __longlong_as_double((long long)all[w * kStCount + threadIdx.x]);
             if (v != 0.0) atomicAdd(reinterpret_cast<double *>(&p.stats[threadIdx.x]), v);
         } else if (threadIdx.x == 0 && blockIdx.x == 0) {
-            atomicAdd(&p.stats[kStEnvSteps], (unsigned long long)p.n_envs);
+            atomicAdd(&p.stats[kStEnvSteps], (unsigned long long)p.n_envs * (unsigned long long)p.n_steps);
         }
     }
     if (errbits) atomicOr(p.err, errbits);

@@ -70,6 +70,12 @@ struct KParams {
     int smem_total;
     int tpe_bm_words;    // thread-per-env kernel: words of the private lattice bitmap (0 = compare-based occupancy)
     unsigned *tpe_counter, *tpe_counter_next;   // thread-per-env kernel: work counters of this / the next launch
+    // thread-per-env kernel, fused multi-step launches (cc_rollout_fused): every output is time-major [n_steps][...]
+    long long obs_env_offset;     // lane-group kernel: the observation rows of env n go to row block n + obs_env_offset of p.obs
+    int n_steps;                  // env-steps per env in this launch (1 for cc_step)
+    long long slice_agents;       // elements of one time slice of a per-agent array: n_envs * A
+    long long slice_envs;         // ... of a per-env array: n_envs
+    long long slice_obs_bytes;    // ... of the observation tensor, in bytes
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -92,6 +98,11 @@ __device__ __forceinline__ U4 philox4x32_10(unsigned c0, unsigned c1, unsigned c
 enum { kStreamReset = 0, kStreamAction = 1 };
 __device__ __forceinline__ U4 draw(const KParams &p, unsigned long long genv, unsigned stream, unsigned idx) {
     return philox4x32_10((unsigned)genv, (unsigned)(genv >> 32), p.t, (stream << 24) | (idx & 0xFFFFFFu),
+                         (unsigned)p.seed, (unsigned)(p.seed >> 32));
+}
+// (same stream at an explicit counter word: step t of a fused multi-step launch draws what launch t would)
+__device__ __forceinline__ U4 draw_at(const KParams &p, unsigned t, unsigned long long genv, unsigned stream, unsigned idx) {
+    return philox4x32_10((unsigned)genv, (unsigned)(genv >> 32), t, (stream << 24) | (idx & 0xFFFFFFu),
                          (unsigned)p.seed, (unsigned)(p.seed >> 32));
 }
 __device__ __forceinline__ int bounded(unsigned r, int n) { return (int)__umulhi(r, (unsigned)n); }
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
     // ---- once per CTA: gather descriptors / LUT, geometry tables -----------------------------------
     const int chunk_pairs = EPW * p.pairs_per_env;
     constexpr bool kPairwise = false;             // (8-byte pair-wise stores measured slower than 16-byte vectors: 0.308 vs 0.276 ms)
-    const bool cached = kCanCache && chunk_pairs <= kDescPairs && (kPairwise || (chunk_pairs % PPV) == 0);
+    const bool cached = kCanCache && chunk_pairs <= kDescPairs && (kPairwise || ((chunk_pairs % PPV) == 0 && (p.obs_env_offset * p.pairs_per_env) % PPV == 0));
     uint4 *desc_sm = reinterpret_cast<uint4 *>(smem + p.off_desc) + threadIdx.x;  // [kDescWords/4][kThreads], conflict-free
     if (kHasObs) {
         if (cached) {
@@ -793,7 +804,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
                 }
             __syncwarp();
             OT *obs = reinterpret_cast<OT *>(p.obs);
-            const long long gp0 = n0 * (long long)p.pairs_per_env;
+            const long long gp0 = (n0 + p.obs_env_offset) * (long long)p.pairs_per_env;   // (offset: time slice of a rollout buffer)
             P2 *out = reinterpret_cast<P2 *>(obs) + gp0;
             const int count = envs_here * p.pairs_per_env;        // output pairs of this group
             if (MODE == kModeReset) {

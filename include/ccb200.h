@@ -195,6 +195,16 @@ int cc_step_host(cc_handle *h, const cc_step_io *io);
  * round-trip, outputs of the last step only). */
 int cc_rollout(cc_handle *h, const cc_step_io *io, int32_t n_steps, void *stream);
 
+/* T steps whose outputs are ALL kept: every output buffer of `io` (obs, reward, agent_flags,
+ * agent_info, env_flags, actions_out) is time-major, [n_steps][...] with the per-step shapes of
+ * cc_step_io; io->actions, when policy == CC_POLICY_EXTERNAL, is [n_steps][N][A] as well.  This is
+ * the loop "policy -> step -> (reset on done)" of the reference's rollouts
+ * (scripts/run_greedy_policy_demo.py:60-95) for N envs.  Where the thread-per-env kernel applies
+ * (crews of 4 or 8, float32 rewards) it is ONE launch: an env's state stays in registers for the T
+ * steps and is read and written once; otherwise one launch per step.  Results are identical to T
+ * calls of cc_step (same RNG counters). */
+int cc_rollout_fused(cc_handle *h, const cc_step_io *io, int32_t n_steps, void *stream);
+
 /* Replaces CollectiveCrossingEnv.reset (collectivecrossing.py:91-159): rejection-sampled
  * placement with the handle's counter-based RNG.  mask: [N] uint8 nullable (NULL = all envs).
  * obs nullable; written for the reset envs only when given. */

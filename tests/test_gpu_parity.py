@@ -76,6 +76,7 @@ ORACLE_CASES = {
     "A3_cassette": (cassette_config, 101),
     "A4": (lambda: crew_config(3, 1, max_steps=40, reward="simple_distance", term="all"), 1000),
     "A5": (lambda: crew_config(3, 2, max_steps=40, term="all"), 258),
+    "A6": (lambda: crew_config(4, 2, max_steps=40), 131),
     "A8_readme": (lambda: readme_config(max_steps=60), 1031),
     "A12": (lambda: crew_config(7, 5, max_steps=40, reward="simple_distance"), 130),
     "A21_odd": (lambda: crew_config(13, 8, max_steps=40), 67),
@@ -496,3 +497,37 @@ def test_rollout_equals_repeated_steps():
         out = b.step(policy="greedy")
     assert torch.equal(a.x, b.x) and torch.equal(a.flags, b.flags) and torch.equal(a.obs, out.obs)
     assert a.stats() == b.stats()
+
+
+@pytest.mark.parametrize("case,policy,obs_dtype", [("A8_readme", "greedy", "float32"), ("A8_readme", "waiting", "int8"), ("A8_readme", "random", "none"),
+                                                   ("A8_readme", "external", "float32"), ("A4", "greedy", "float32"), ("A5", "waiting", "int8"), ("A6", "greedy", "int8")])
+def test_fused_rollout_equals_repeated_steps(case, policy, obs_dtype):
+    """cc_rollout_fused (one launch, state in registers for T steps where the thread-per-env kernel
+    applies; one launch per step otherwise) returns, for every step, exactly what T calls of step() return."""
+    make_cfg, n = ORACLE_CASES[case]
+    cfg = make_cfg()
+    T = 37
+    rng = np.random.default_rng(5)
+    x, y, f, s = random_states(cfg, n, rng)
+    envs = [make_env(cfg, n, seed=9, global_env_offset=77, obs_dtype=obs_dtype, auto_reset=True, with_info=True) for _ in range(2)]
+    for e in envs:
+        e.set_state(*(torch.from_numpy(v).cuda() for v in (x, y, f, s)))
+    A = envs[0].num_agents
+    acts = torch.from_numpy(rng.integers(0, 5, size=(T, n, A)).astype(np.int8)).cuda() if policy == "external" else None
+    traj = envs[0].rollout_trajectory(T, policy=policy, actions=acts)
+    assert envs[0].last_kernel == ("threads" if case in ("A8_readme", "A4") else "lanes")
+    assert envs[0].launch_count == (1 if case in ("A8_readme", "A4") else T)
+    for t in range(T):
+        out = envs[1].step(acts[t] if acts is not None else None, policy=policy)
+        for name, got, want in (("reward", traj["reward"][t], out.reward), ("agent_flags", traj["agent_flags"][t], out.agent_flags),
+                                ("agent_info", traj["agent_info"][t], out.agent_info), ("env_flags", traj["env_flags"][t], out.env_flags),
+                                ("actions", traj["actions"][t], out.actions)):
+            assert torch.equal(got, want), f"{case}/{policy}/t={t}: {name}"
+        if obs_dtype != "none":
+            assert torch.equal(traj["obs"][t], out.obs), f"{case}/{policy}/t={t}: obs"
+    for name in ("x", "y", "flags", "step_count", "episode_return"):
+        assert torch.equal(getattr(envs[0], name), getattr(envs[1], name)), name
+    assert envs[0].stats() == pytest.approx(envs[1].stats()) and envs[0].step_counter == envs[1].step_counter
+    for e in envs:
+        e.check_error()
+        e.close()
