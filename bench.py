@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--obs-dtype", default="float32", choices=["float32", "int8", "none"])
     ap.add_argument("--policy", default="greedy", choices=["greedy", "waiting", "random"])
+    ap.add_argument("--steps-per-launch", type=int, default=16,
+                    help="env-steps fused into one launch (cc_rollout_fused); 1 = one launch per step")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
@@ -57,7 +59,10 @@ def config_dict(args, n_total):
                     f"IndividualAtDestination, MaxSteps 100, {args.policy} baseline policy in-kernel, auto-reset; "
                     f"{args.envs} envs per GPU",
         "envs_total": n_total, "envs_per_gpu": args.envs, "agents_per_env": 8, "obs_dtype": args.obs_dtype,
-        "policy": args.policy, "l2_policy": "inputs larger than L2 (no flush)" if args.envs >= 1 << 19 else "working set may fit L2",
+        "policy": args.policy, "steps_per_launch": args.steps_per_launch,
+        "launch": (f"cc_rollout_fused: {args.steps_per_launch} env-steps per launch, state in registers, every step's outputs written "
+                   f"([T, N, ...] buffers); steps % T as single-step launches" if args.steps_per_launch > 1 else "cc_step: one launch per env-step"),
+        "l2_policy": "inputs larger than L2 (no flush)" if args.envs >= 1 << 19 else "working set may fit L2",
         "parallelism": "independent env shards, one process per GPU, no data-path collective",
     }
 
@@ -238,12 +243,18 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def time_steps(env, torch, dist, args, steps, policy, world):
+def time_steps(env, torch, dist, args, steps, policy, world, per_launch=1):
+    """EXACTLY `steps` env-steps of every env: steps // per_launch fused launches of `per_launch` steps
+    (all of whose observations, rewards and flags are written) and steps % per_launch single-step launches."""
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    if per_launch > 1:
+        for _ in range(steps // per_launch):
+            env.rollout_trajectory(per_launch, policy=policy)
+        steps = steps % per_launch
     for _ in range(steps):
         env.step(policy=policy)
     e1.record()
@@ -285,8 +296,11 @@ def run_ours(args):
     env = sharded.env
     assert sharded.count == n and sharded.offset == rank * n
     env.reset()
+    T = max(1, args.steps_per_launch)
     for _ in range(args.warmup):
         env.step(policy=args.policy)
+    if T > 1:
+        env.rollout_trajectory(T, policy=args.policy)   # allocates the [T, N, ...] output buffers, warms the fused launch
     torch.cuda.synchronize()
     env.reset_stats()
     launches0 = env.launch_count
@@ -294,7 +308,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.mark_begin()
-    ms = time_steps(env, torch, dist, args, args.steps, args.policy, world)
+    ms = time_steps(env, torch, dist, args, args.steps, args.policy, world, T)
     if sampler:
         sampler.mark_end()
     clocks = sampler.stop() if sampler else None
@@ -311,20 +325,26 @@ def run_ours(args):
         peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    bytes_per_launch = env.algorithmic_bytes_per_env_step() * n
-    achieved = bytes_per_launch / (ms / args.steps * 1e-3) / 1e9
+    # algorithmic bytes: 12A+17+s_obs*A*(6+4A) per env-step of a single-step launch; a fused launch of T
+    # steps keeps the state in registers, so its state term 2(3A+4)+8 is paid once per T steps
+    b1 = env.algorithmic_bytes_per_env_step()
+    bT = b1 - (2 * (3 * A + 4) + 8) * (1.0 - 1.0 / T)
+    fused_steps = (args.steps // T) * T if T > 1 else 0
+    total_bytes = (bT * fused_steps + b1 * (args.steps - fused_steps)) * n
+    achieved = total_bytes / (ms * 1e-3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get(f"{args.obs_dtype}_{args.policy}_{n}")
+            traffic = json.loads(tp.read_text()).get(f"{args.obs_dtype}_{args.policy}_{n}_T{T}")
         except Exception:
             traffic = None
     kernel_name = ("ccb::cc_step_tpe_kernel<8,%s>" if env.last_kernel == "threads" else "ccb::cc_kernel<8,1,%s,step>") % {"float32": 4, "int8": 1, "none": 0}[args.obs_dtype]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": kernel_name,
-                "algorithmic_bytes_per_env_step": env.algorithmic_bytes_per_env_step(),
-                "formula": "12A+17+s_obs*A*(6+4A), A=8 (SURVEY.md 8d)"}
+                "algorithmic_bytes_per_env_step": total_bytes / (n * args.steps), "steps_per_launch": T,
+                "algorithmic_bytes_per_launch": bT * T * n if T > 1 else b1 * n,
+                "formula": "12A+17+s_obs*A*(6+4A), A=8 (SURVEY.md 8d); in a fused launch of T steps the state term 2(3A+4)+8 is paid once per T steps"}
 
     # ---- e2e: host buffers through the C ABI (cc_policy_actions -> D2H -> cc_step_host) ----------
     host = env.make_host_buffers(pinned=True)
@@ -398,6 +418,7 @@ def secondary(args, torch, dist, cfg):
     M = 1 << 20
     runs = (
         # tag, config, envs, obs dtype, policy, kernel, timed steps
+        ("1M_envs_fp32_greedy_single_step_launches", cfg, M, "float32", "greedy", "auto", 50),
         ("cfg2_65536_envs_fp32_greedy", cfg, 65536, "float32", "greedy", "auto", 50),
         ("1M_envs_int8_greedy", cfg, M, "int8", "greedy", "auto", 50),
         ("1M_envs_noobs_greedy", cfg, M, "none", "greedy", "auto", 50),
@@ -420,6 +441,31 @@ def secondary(args, torch, dist, cfg):
         a = env.num_agents
         out[tag] = {"agent_steps_per_sec": n * a * steps / (ms * 1e-3), "ms_per_step": ms / steps, "algorithmic_GBps": b / (ms / steps * 1e-3) / 1e9,
                     "kernel": env.last_kernel, "agents_per_env": a, "envs": n}
+        env.close()
+        del env
+        torch.cuda.empty_cache()
+    # fused multi-step launches (cc_rollout_fused): T env-steps per env per launch, the state stays in registers;
+    # every step's observations, rewards and flags are still written ([T, N, ...] buffers).  Algorithmic bytes per
+    # env-step: the state term 2(3A+4)+8 of SURVEY.md 8d is paid once per T steps.
+    for T in (4, 16):
+        env = BatchedCollectiveCrossing(cfg, M, dev, seed=1, obs_dtype="float32", auto_reset=True)
+        env.reset()
+        env.rollout_trajectory(T, policy="greedy")
+        launches = 12
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(launches):
+            env.rollout_trajectory(T, policy="greedy")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (launches * T)
+        env.check_error()
+        a = env.num_agents
+        bytes_step = a + (2 * (3 * a + 4) + 8) / T + 5 * a + 1 + 4 * a * (6 + 4 * a)
+        out[f"fused_rollout_T{T}_1M_envs_fp32_greedy"] = {
+            "agent_steps_per_sec": M * a / (ms * 1e-3), "ms_per_step": ms, "algorithmic_GBps": bytes_step * M / (ms * 1e-3) / 1e9,
+            "algorithmic_bytes_per_env_step": bytes_step, "kernel": env.last_kernel, "agents_per_env": a, "envs": M, "steps_per_launch": T}
         env.close()
         del env
         torch.cuda.empty_cache()
