@@ -22,6 +22,10 @@
 #ifndef CCB_TPE_TMA
 #define CCB_TPE_TMA 1          // float32 rows leave the SM through cp.async.bulk (TMA) instead of st.global, see DESIGN.md §3
 #endif
+#ifndef CCB_TPE_CONST_REGS
+#define CCB_TPE_CONST_REGS 0   // TMA gather: 1 = lanes whose pair is K1 / K2 / M keep it in a register (predicated load, no bank
+                               // conflicts, 4 instructions per pair); 0 = every lane loads from the template (1 instruction, 2-way conflicts)
+#endif
 #ifndef CCB_TPE_STAGGER_NS
 #define CCB_TPE_STAGGER_NS 0
 #endif
@@ -146,18 +150,23 @@ __device__ __forceinline__ void tpe_emit_group_tma(const unsigned *lut, unsigned
     using L = TpeLayout<A, OBS>;
     static_assert(L::kImgRing == 3, "the env loop is unrolled by the ring size");
     // src[j]: shared address, inside the template of the env being emitted, of the pair that feeds output
-    // pair lane + 32 j (the same offsets for every env) — or 0xFFFFFFFF when that pair is one of the constants
-    // K1, K2, M: such a lane keeps the constant in val[j] for the whole group and makes NO shared-memory
-    // access (the predicated load below), which is what keeps the gather free of bank conflicts: the other
-    // lanes of a half-warp read consecutive template pairs.
+    // pair lane + 32 j (the same offsets for every env).  With CCB_TPE_CONST_REGS a lane whose pair is one of
+    // the constants K1, K2, M (src = 0xFFFFFFFF) keeps it in val[j] for the whole group and makes no
+    // shared-memory access, so the other lanes of a half-warp read consecutive template pairs without bank
+    // conflicts; measured, the conflicts cost nothing and the predication 400 instructions per 32 envs.
     unsigned src[L::kImgInstr];
     unsigned long long val[L::kImgInstr];
 #pragma unroll
     for (int j = 0; j < L::kImgInstr; ++j) {
         const unsigned d = lut[j * 32 + lane];
+#if CCB_TPE_CONST_REGS
         src[j] = (d >> 31) ? 0xFFFFFFFFu : sbase + d;
         const uint2 c = (d & 3u) == 1u ? kc.k1 : ((d & 3u) == 2u ? kc.k2 : kc.m);
         val[j] = (unsigned long long)c.x | ((unsigned long long)c.y << 32);
+#else
+        src[j] = sbase + ((d >> 31) ? (unsigned)((2 * A - 1 + (int)(d & 3u)) * L::PSZ) : d);   // constants follow the agent table
+        val[j] = 0ull;
+#endif
     }
     const unsigned img0 = sbase + L::kTplBytesPerWarp;                   // image ring of this warp
     const unsigned islot = img0 + 8u * lane;                             // this lane's pair slot of image 0
@@ -170,8 +179,12 @@ __device__ __forceinline__ void tpe_emit_group_tma(const unsigned *lut, unsigned
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < L::kImgInstr; ++j) {
+#if CCB_TPE_CONST_REGS
             asm volatile("{\n\t.reg .pred pl;\n\tsetp.ne.u32 pl, %1, 0xFFFFFFFF;\n\t@pl ld.shared.b64 %0, [%2];\n\t}"
                          : "+l"(val[j]) : "r"(src[j]), "r"(src[j] + t_imm));
+#else
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(val[j]) : "r"(src[j] + t_imm));
+#endif
             if (j * 32 + 32 <= L::PPE || lane + j * 32 < L::PPE)
                 asm volatile("st.shared.b64 [%0], %1;" ::"r"(islot + buf + 256u * j), "l"(val[j]) : "memory");
         }
@@ -194,7 +207,7 @@ __device__ __forceinline__ void tpe_emit_group_tma(const unsigned *lut, unsigned
         emit_env((unsigned)L::TSB, (unsigned)L::kImgBytes);
         emit_env(2u * L::TSB, 2u * L::kImgBytes);
 #pragma unroll
-        for (int j = 0; j < L::kImgInstr; ++j) src[j] = src[j] == 0xFFFFFFFFu ? src[j] : src[j] + 3u * L::TSB;
+        for (int j = 0; j < L::kImgInstr; ++j) src[j] = (CCB_TPE_CONST_REGS && src[j] == 0xFFFFFFFFu) ? src[j] : src[j] + 3u * L::TSB;
     }
     if (e < envs_here) emit_env(0u, 0u);                                              // 32 = 10 x 3 + 2
     if (e + 1 < envs_here) emit_env((unsigned)L::TSB, (unsigned)L::kImgBytes);
