@@ -193,23 +193,26 @@ bool aligned_to(const void *q, uintptr_t a) { return (reinterpret_cast<uintptr_t
 // which step launches the thread-per-env kernel can serve
 bool tpe_eligible(const cc_handle *h, const cc_step_io *io) {
     const int A = h->A;
-    if (A != 8 && A != 4) return false;
+    if (A < 1 || A > 8) return false;
     if (io->order || io->reward_dtype != CC_REWARD_F32) return false;      // dict order / float64 rewards: lane-group kernel
     if (io->obs_dtype == CC_OBS_INT8 && A != 8) return false;              // an env's int8 block must be whole 16-byte vectors
-    const void *rows[] = {h->x, h->y, h->flags, io->actions, io->actions_out, io->agent_flags, io->agent_info};
-    for (const void *q : rows)
-        if (q && !aligned_to(q, (uintptr_t)A)) return false;
-    return aligned_to(io->reward, 16) && aligned_to(h->step, 4) && aligned_to(h->ep_ret, 4);
+    if (A == 8 || A == 4) {                                                // rows are moved as one aligned word
+        const void *rows[] = {h->x, h->y, h->flags, io->actions, io->actions_out, io->agent_flags, io->agent_info};
+        for (const void *q : rows)
+            if (q && !aligned_to(q, (uintptr_t)A)) return false;
+    }
+    return aligned_to(io->reward, A % 4 == 0 ? 16 : 4) && aligned_to(h->step, 4) && aligned_to(h->ep_ret, 4);
 }
 
 int launch_tpe(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s) {
+#define CCB_TPE_CASES(A_)                                                                   \
+    case A_ * 8 + CC_OBS_NONE: return launch_tpe_t<A_, CC_OBS_NONE>(h, p, s);                   \
+    case A_ * 8 + CC_OBS_FP32: return launch_tpe_t<A_, CC_OBS_FP32>(h, p, s);
     switch (h->A * 8 + obs_dtype) {
-    case 8 * 8 + CC_OBS_NONE: return launch_tpe_t<8, CC_OBS_NONE>(h, p, s);
+        CCB_TPE_CASES(1) CCB_TPE_CASES(2) CCB_TPE_CASES(3) CCB_TPE_CASES(4) CCB_TPE_CASES(5) CCB_TPE_CASES(6) CCB_TPE_CASES(7) CCB_TPE_CASES(8)
     case 8 * 8 + CC_OBS_INT8: return launch_tpe_t<8, CC_OBS_INT8>(h, p, s);
-    case 8 * 8 + CC_OBS_FP32: return launch_tpe_t<8, CC_OBS_FP32>(h, p, s);
-    case 4 * 8 + CC_OBS_NONE: return launch_tpe_t<4, CC_OBS_NONE>(h, p, s);
-    case 4 * 8 + CC_OBS_FP32: return launch_tpe_t<4, CC_OBS_FP32>(h, p, s);
     }
+#undef CCB_TPE_CASES
     return fail(CC_ERR_UNSUPPORTED, "no thread-per-env kernel for %d agents, obs_dtype %d", h->A, obs_dtype);
 }
 
@@ -238,8 +241,8 @@ int step_on(cc_handle *h, const cc_step_io *io, cudaStream_t s, int n_steps = 1,
     p.policy = io->policy; p.auto_reset = io->auto_reset != 0; p.reward_f64 = io->reward_dtype == CC_REWARD_F64;
     const bool can_tpe = obs_env_offset == 0 && tpe_eligible(h, io);
     if (h->variant == CC_KERNEL_THREADS && !can_tpe)
-        return fail(CC_ERR_UNSUPPORTED, "CC_KERNEL_THREADS was requested but this step is not eligible (needs 4 or 8 agents, agent order, "
-                                        "float32 rewards, rows aligned to the crew size)");
+        return fail(CC_ERR_UNSUPPORTED, "CC_KERNEL_THREADS was requested but this step is not eligible (needs at most 8 agents, agent order, "
+                                        "float32 rewards, int8 rows only for 8 agents, word-aligned rows for 4 or 8 agents)");
     const bool use_tpe = can_tpe && h->variant != CC_KERNEL_LANES;
     int rc = use_tpe ? launch_tpe(h, p, io->obs_dtype, s) : launch<ccb::kModeStep>(h, p, io->obs_dtype, s);
     if (n_steps > 1 && !use_tpe) return fail(CC_ERR_UNSUPPORTED, "fused multi-step launches need the thread-per-env kernel");

@@ -63,7 +63,7 @@ struct TpeLayout {
     // observation block (A rows = kImgBytes) and leave the SM as bulk asynchronous copies (TMA): stores
     // issued with st.global stall the whole load/store pipe of the SM while HBM pushes back, and with it
     // the shared-memory work of the warps that are stepping envs (profiles/probes/lsu_coupling_probe.cu)
-    static constexpr bool kTma = OBS == CC_OBS_FP32 && CCB_TPE_TMA != 0;
+    static constexpr bool kTma = OBS == CC_OBS_FP32 && CCB_TPE_TMA != 0 && (PPE * PSZ) % 16 == 0;   // bulk copies move multiples of 16 bytes: even crews
     static constexpr int kImgBytes = PPE * PSZ;          // 1216 B for A = 8; a multiple of 16 whenever A is even
     static constexpr int kImgRing = 3;
     static constexpr int kImgInstr = (PPE + 31) / 32;    // warp instructions that cover an env's pairs
@@ -105,14 +105,19 @@ __device__ __forceinline__ unsigned tpe_pair_offset(int P) {
     return (unsigned)((src >= 0 ? src : 2 * A - 1 - src) * PSZ);
 }
 
-// A bytes of env `env` of an [N][A] byte array: one 8-byte (A = 8) or 4-byte (A = 4) word per thread.
+// A bytes of env `env` of an [N][A] byte array: one 8-byte (A = 8) or 4-byte (A = 4) word per thread, bytes otherwise.
 // Loading (packed) and unpacking are separate so that the next group's record can be fetched early.
 template <int A>
 __device__ __forceinline__ uint2 tpe_fetch_row(const void *base, int env) {
-    static_assert(A == 8 || A == 4, "rows are fetched as one aligned word");
     const unsigned char *q = static_cast<const unsigned char *>(base) + (size_t)env * A;
     if constexpr (A == 8) return *reinterpret_cast<const uint2 *>(q);
-    else return make_uint2(*reinterpret_cast<const unsigned *>(q), 0u);
+    else if constexpr (A == 4) return make_uint2(*reinterpret_cast<const unsigned *>(q), 0u);
+    else {   // other crews: rows are not word-aligned, byte loads (the warp still covers one contiguous run of 32 A bytes)
+        uint2 w = make_uint2(0u, 0u);
+#pragma unroll
+        for (int k = 0; k < A; ++k) (k < 4 ? w.x : w.y) |= (unsigned)q[k] << (8 * (k & 3));
+        return w;
+    }
 }
 template <int A>
 __device__ __forceinline__ void tpe_unpack_row(uint2 w, unsigned (&v)[A]) {

@@ -200,7 +200,7 @@ int cc_rollout(cc_handle *h, const cc_step_io *io, int32_t n_steps, void *stream
  * cc_step_io; io->actions, when policy == CC_POLICY_EXTERNAL, is [n_steps][N][A] as well.  This is
  * the loop "policy -> step -> (reset on done)" of the reference's rollouts
  * (scripts/run_greedy_policy_demo.py:60-95) for N envs.  Where the thread-per-env kernel applies
- * (crews of 4 or 8, float32 rewards) it is ONE launch: an env's state stays in registers for the T
+ * (crews of at most 8, float32 rewards) it is ONE launch: an env's state stays in registers for the T
  * steps and is read and written once; otherwise one launch per step.  Results are identical to T
  * calls of cc_step (same RNG counters). */
 int cc_rollout_fused(cc_handle *h, const cc_step_io *io, int32_t n_steps, void *stream);
@@ -240,7 +240,7 @@ int64_t cc_launch_count(const cc_handle *h);
 /* Which work mapping cc_step uses.  Both produce identical results (tests/test_gpu_parity.py
  * runs every case through both):
  *   CC_KERNEL_LANES    one lane per agent, 4-32 lanes per env (any crew size, dict order, float64 rewards);
- *   CC_KERNEL_THREADS  one thread per env (crews of 4 or 8, agent order, float32 rewards);
+ *   CC_KERNEL_THREADS  one thread per env (crews of at most 8, agent order, float32 rewards; int8 rows: 8 agents);
  *   CC_KERNEL_AUTO     THREADS where eligible, else LANES (default).
  * Requesting CC_KERNEL_THREADS makes ineligible steps fail with CC_ERR_UNSUPPORTED. */
 enum { CC_KERNEL_AUTO = 0, CC_KERNEL_LANES = 1, CC_KERNEL_THREADS = 2 };

@@ -73,10 +73,12 @@ def test_thread_per_env_kernel_replays_golden(name):
 # ---- seeded comparison against the oracle, every kernel instantiation ----------------------------
 ORACLE_CASES = {
     "A1": (lambda: crew_config(1, 0, max_steps=25), 37),
+    "A2": (lambda: crew_config(1, 1, max_steps=30, reward="binary"), 75),
     "A3_cassette": (cassette_config, 101),
     "A4": (lambda: crew_config(3, 1, max_steps=40, reward="simple_distance", term="all"), 1000),
     "A5": (lambda: crew_config(3, 2, max_steps=40, term="all"), 258),
     "A6": (lambda: crew_config(4, 2, max_steps=40), 131),
+    "A7": (lambda: crew_config(4, 3, max_steps=40, reward="constant_negative", term="all"), 260),
     "A8_readme": (lambda: readme_config(max_steps=60), 1031),
     "A12": (lambda: crew_config(7, 5, max_steps=40, reward="simple_distance"), 130),
     "A21_odd": (lambda: crew_config(13, 8, max_steps=40), 67),
@@ -99,7 +101,8 @@ def _compare_step(env, orc, res, out, tag, obs_np):
 
 
 # every case with the default mapping, and the crews the thread-per-env kernel takes also with the lane-group one
-CASE_KERNELS = [(c, "auto") for c in ORACLE_CASES] + [("A4", "lanes"), ("A8_readme", "lanes")]
+SMALL_CREWS = ("A1", "A2", "A3_cassette", "A4", "A5", "A6", "A7", "A8_readme")   # served by the thread-per-env kernel
+CASE_KERNELS = [(c, "auto") for c in ORACLE_CASES] + [(c, "lanes") for c in SMALL_CREWS]
 
 
 @pytest.mark.parametrize("policy", ["random", "greedy", "waiting"])
@@ -115,8 +118,8 @@ def test_device_matches_oracle_with_auto_reset(case, kernel, policy):
     x, y, f, s = random_states(cfg, n, rng)
     seed, offset = 1234567 + n, 10_000_000_000 + n  # offset > 2**32: both counter words matter
     obs_dtype = "float32" if policy == "greedy" else "int8"
-    if case == "A4" and kernel == "auto":
-        obs_dtype = "float32"   # a 4-agent env's int8 block is not a whole number of 16-byte vectors
+    if case in SMALL_CREWS and case != "A8_readme" and kernel == "auto":
+        obs_dtype = "float32"   # int8 rows go through the thread-per-env kernel only for 8 agents (whole 16-byte vectors)
     env = make_env(cfg, n, seed=seed, global_env_offset=offset, obs_dtype=obs_dtype, auto_reset=True, with_info=True, kernel=kernel)
     orc = oracle.OracleEnvs(low, n, seed=seed, global_env_offset=offset)
     env.set_state(*(torch.from_numpy(v).cuda() for v in (x, y, f, s)))
@@ -127,7 +130,7 @@ def test_device_matches_oracle_with_auto_reset(case, kernel, policy):
         res = orc.step(policy=policy, auto_reset=True, obs_dtype=_abi.OBS_FP32 if obs_dtype == "float32" else _abi.OBS_INT8)
         _compare_step(env, orc, res, out, f"{case}/{policy}/t={t}", np.float32 if obs_dtype == "float32" else np.int8)
     env.check_error()
-    assert env.last_kernel == ("threads" if kernel == "auto" and case in ("A4", "A8_readme") else "lanes")
+    assert env.last_kernel == ("threads" if kernel == "auto" and case in SMALL_CREWS else "lanes")
     st, want = env.stats(), orc.stats.as_dict()
     for k in ("env_steps", "episodes", "terminated_all", "truncated_all", "arrivals", "episode_length_sum"):
         assert st[k] == want[k], (k, st[k], want[k])
@@ -165,7 +168,7 @@ def test_device_external_actions_and_custom_order_match_oracle(case):
 
 
 @pytest.mark.parametrize("obs_dtype", ["none", "int8", "float32"])
-@pytest.mark.parametrize("case", ["A4", "A8_readme"])
+@pytest.mark.parametrize("case", list(SMALL_CREWS))
 def test_thread_per_env_kernel_external_actions_match_oracle(case, obs_dtype):
     """External action tensors (incl. out-of-range values that must raise), no auto-reset, ragged
     env counts: the thread-per-env kernel against the oracle and against the lane-group kernel."""
@@ -176,7 +179,7 @@ def test_thread_per_env_kernel_external_actions_match_oracle(case, obs_dtype):
     low = lower_config(cfg)
     A = low.num_agents
     if obs_dtype == "int8" and A != 8:
-        pytest.skip("int8 rows of a 4-agent env are not 16-byte multiples: served by the lane-group kernel")
+        pytest.skip("int8 rows of other crews are not 16-byte multiples: served by the lane-group kernel")
     code = {"none": _abi.OBS_NONE, "int8": _abi.OBS_INT8, "float32": _abi.OBS_FP32}[obs_dtype]
     for n in (1, 31, 33, 517):
         rng = np.random.default_rng(n)
@@ -211,7 +214,7 @@ def test_thread_per_env_kernel_external_actions_match_oracle(case, obs_dtype):
 
 
 def test_thread_per_env_request_on_ineligible_step_raises():
-    env = make_env(crew_config(3, 2), 8, obs_dtype="none", kernel="threads")
+    env = make_env(crew_config(7, 5), 8, obs_dtype="none", kernel="threads")
     env.reset()
     with pytest.raises(NotImplementedError, match="CC_KERNEL_THREADS"):
         env.step(policy="greedy")
@@ -500,7 +503,8 @@ def test_rollout_equals_repeated_steps():
 
 
 @pytest.mark.parametrize("case,policy,obs_dtype", [("A8_readme", "greedy", "float32"), ("A8_readme", "waiting", "int8"), ("A8_readme", "random", "none"),
-                                                   ("A8_readme", "external", "float32"), ("A4", "greedy", "float32"), ("A5", "waiting", "int8"), ("A6", "greedy", "int8")])
+                                                   ("A8_readme", "external", "float32"), ("A4", "greedy", "float32"), ("A5", "waiting", "int8"), ("A6", "greedy", "int8"),
+                                                   ("A3_cassette", "greedy", "float32"), ("A7", "waiting", "float32"), ("A12", "greedy", "float32")])
 def test_fused_rollout_equals_repeated_steps(case, policy, obs_dtype):
     """cc_rollout_fused (one launch, state in registers for T steps where the thread-per-env kernel
     applies; one launch per step otherwise) returns, for every step, exactly what T calls of step() return."""
@@ -515,8 +519,9 @@ def test_fused_rollout_equals_repeated_steps(case, policy, obs_dtype):
     A = envs[0].num_agents
     acts = torch.from_numpy(rng.integers(0, 5, size=(T, n, A)).astype(np.int8)).cuda() if policy == "external" else None
     traj = envs[0].rollout_trajectory(T, policy=policy, actions=acts)
-    assert envs[0].last_kernel == ("threads" if case in ("A8_readme", "A4") else "lanes")
-    assert envs[0].launch_count == (1 if case in ("A8_readme", "A4") else T)
+    fused = case in SMALL_CREWS and (obs_dtype != "int8" or case == "A8_readme")
+    assert envs[0].last_kernel == ("threads" if fused else "lanes")
+    assert envs[0].launch_count == (1 if fused else T)
     for t in range(T):
         out = envs[1].step(acts[t] if acts is not None else None, policy=policy)
         for name, got, want in (("reward", traj["reward"][t], out.reward), ("agent_flags", traj["agent_flags"][t], out.agent_flags),
