@@ -95,6 +95,16 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     off += needs_bitmap ? round_up(ccb::kWarpsPerCta * h->epw * p.walk_words * 4, 16) : 0;
     p.off_desc = off;
     off += (obs_dtype != CC_OBS_NONE && h->lpe <= 16) ? ccb::kDescWords * 4 * ccb::kThreads : 0;
+    // int8 rows of big crews (one env per warp): shifted template copies + vector lists (cc_kernels.cuh)
+    const int env_bytes = h->A * (6 + 4 * h->A);
+    if (obs_dtype == CC_OBS_INT8 && h->lpe == 32 && h->epw == 1 && env_bytes % 16 == 0 && env_bytes / 16 < 65536) {
+        p.nvec_env = env_bytes / 16;
+        p.shift_tst = round_up(14 + (2 * h->A + 4) * 2 + 16, 16);
+        p.off_shift = off;
+        off += ccb::kWarpsPerCta * 8 * p.shift_tst;
+        p.off_vlist = off;
+        off += round_up(p.nvec_env * 6 + 16, 16);
+    }
     p.smem_total = off;
     p.n_groups = (h->n_envs + h->epw - 1) / h->epw;
 }

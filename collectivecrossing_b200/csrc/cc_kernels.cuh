@@ -71,6 +71,13 @@ struct KParams {
     int tpe_bm_words;    // thread-per-env kernel: words of the private lattice bitmap (0 = compare-based occupancy)
     unsigned *tpe_counter, *tpe_counter_next;   // thread-per-env kernel: work counters of this / the next launch
     // thread-per-env kernel, fused multi-step launches (cc_rollout_fused): every output is time-major [n_steps][...]
+    // lane-group kernel, int8 rows of one-env-per-warp crews (A > 16) whose env block is a whole number of 16-byte
+    // vectors: 8 copies of the row template, shifted by 0, 2, ..., 14 bytes, so that most output vectors are ONE
+    // aligned 16-byte shared-memory load (shift_tst = 0: not used)
+    int shift_tst;                // bytes of one shifted copy (multiple of 16)
+    int off_shift;                // [warp][8][shift_tst]
+    int off_vlist;                // unsigned plain[nvec_env] then unsigned short special[nvec_env], then 2 counters
+    int nvec_env;                 // 16-byte vectors of an env's observation block
     long long obs_env_offset;     // lane-group kernel: the observation rows of env n go to row block n + obs_env_offset of p.obs
     int n_steps;                  // env-steps per env in this launch (1 for cc_step)
     long long slice_agents;       // elements of one time slice of a per-agent array: n_envs * A
@@ -337,6 +344,41 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
         for (int e = T.lane; e < EPW; e += 32) {   // the constant pairs of every env template of this warp
             P2 *t = stage + e * (2 * A + 4);
             t[0] = mk_pair<OT>(0, 0); t[1] = mk_pair<OT>(p.DC, p.D); t[2] = mk_pair<OT>(p.DL, p.DR); t[2 * A + 3] = mk_pair<OT>(-1, -1);
+        }
+    }
+    // int8 rows of big crews: classify the env block's 16-byte vectors once.  Row i of an env is the row template
+    // [P K1 K2 S_0a ... S_(A-1)b] with pair 0 replaced by S_ia and the own block by M, so a vector that lies inside
+    // one row and touches neither pair 0 nor the own block is 16 consecutive template bytes: it is loaded with one
+    // aligned 16-byte load from the copy of the template whose shift matches the row's alignment ("plain" list:
+    // vector | offset << 16).  The others ("special" list) are gathered pair by pair through the LUT.
+    constexpr bool kShiftable = kHasObs && OBS == CC_OBS_INT8 && LPE == 32 && MODE != kModeReset;
+    unsigned *vplain = reinterpret_cast<unsigned *>(smem + p.off_vlist);
+    unsigned short *vspecial = reinterpret_cast<unsigned short *>(vplain + p.nvec_env);
+    int *vcount = reinterpret_cast<int *>(smem + p.off_vlist + p.nvec_env * 6 + 8 - (p.nvec_env * 6) % 8);   // {plain, special}
+    unsigned char *shifted = smem + p.off_shift + warp * 8 * p.shift_tst;
+    const bool shift_rows = kShiftable && p.shift_tst > 0;
+    if (shift_rows) {
+        const int lrow = 6 + 4 * A;
+        if (warp == 0) {
+            int n_plain = 0, n_special = 0;
+            for (int v0 = 0; v0 < p.nvec_env; v0 += 32) {
+                const int v = v0 + T.lane, b0 = 16 * v, i0 = b0 / lrow, r0 = b0 - i0 * lrow;
+                const bool in_range = v < p.nvec_env;
+                const bool special = (b0 + 15) / lrow != i0 || r0 < 2 || (r0 < 10 + 4 * i0 && r0 + 16 > 6 + 4 * i0);
+                const int c = ((16 - (r0 & 15)) >> 1) & 7;                     // copy whose shift aligns template byte r0
+                const unsigned plain_mask = __ballot_sync(kFull, in_range && !special), special_mask = __ballot_sync(kFull, in_range && special);
+                const unsigned below = (1u << T.lane) - 1u;
+                if (in_range && !special) vplain[n_plain + __popc(plain_mask & below)] = (unsigned)v | ((unsigned)(c * p.shift_tst + 2 * c + r0) << 16);
+                if (in_range && special) vspecial[n_special + __popc(special_mask & below)] = (unsigned short)v;
+                n_plain += __popc(plain_mask);
+                n_special += __popc(special_mask);
+            }
+            if (T.lane == 0) { vcount[0] = n_plain; vcount[1] = n_special; }
+        }
+        // constant head of every copy: template bytes 2..5 = K1, K2 (bytes 0..1, pair 0, are never read from a copy)
+        if (T.lane < 8) {
+            unsigned char *t = shifted + T.lane * p.shift_tst + 2 * T.lane;
+            t[2] = (unsigned char)p.DC; t[3] = (unsigned char)p.D; t[4] = (unsigned char)p.DL; t[5] = (unsigned char)p.DR;
         }
     }
     for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
@@ -801,6 +843,16 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
                 if (avalid[k]) {
                     tstage[2 * aidx[k]] = mk_pair<OT>((int)(int8_t)(pos[k] >> 8), (int)(int8_t)(pos[k] & 0xffu));
                     tstage[2 * aidx[k] + 1] = mk_pair<OT>(aidx[k] < p.B ? 0 : 1, (int)(fl[k] & 1u));
+                    if (shift_rows) {
+                        // the agent's 4 bytes into the 8 shifted copies (template byte 6 + 4a at copy byte 2c + 6 + 4a)
+                        const unsigned lo = (pos[k] >> 8 & 0xffu) | ((pos[k] & 0xffu) << 8), hi = (aidx[k] < p.B ? 0u : 1u) | ((fl[k] & 1u) << 8);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            unsigned char *d = shifted + c * p.shift_tst + 2 * c + 6 + 4 * aidx[k];
+                            if (c & 1) *reinterpret_cast<unsigned *>(d) = lo | (hi << 16);
+                            else { *reinterpret_cast<unsigned short *>(d) = (unsigned short)lo; *reinterpret_cast<unsigned short *>(d + 2) = (unsigned short)hi; }
+                        }
+                    }
                 }
             __syncwarp();
             OT *obs = reinterpret_cast<OT *>(p.obs);
@@ -843,6 +895,22 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
                             }
                             if (j * 32 + 32 <= nvec || T.lane + j * 32 < nvec) __stcs(outv + 32 * j, pk.u);
                         }
+                    }
+                }
+            } else if (shift_rows) {
+                if constexpr (kShiftable) {
+                    uint4 *outv = reinterpret_cast<uint4 *>(out);   // (the env block is a whole number of 16-byte vectors)
+                    const int n_plain = vcount[0], n_special = vcount[1];
+                    for (int idx = T.lane; idx < n_plain; idx += 32) {
+                        const unsigned e = vplain[idx];
+                        __stcs(outv + (e & 0xffffu), *reinterpret_cast<const uint4 *>(shifted + (e >> 16)));
+                    }
+                    for (int idx = T.lane; idx < n_special; idx += 32) {
+                        const int v = vspecial[idx];
+                        union { uint4 u; P2 e[PPV]; } pk;
+#pragma unroll
+                        for (int c = 0; c < PPV; ++c) pk.e[c] = stage[lut[v * PPV + c]];
+                        __stcs(outv + v, pk.u);
                     }
                 }
             } else if (cached) {
