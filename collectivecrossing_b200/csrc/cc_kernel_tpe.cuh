@@ -7,10 +7,13 @@
 // instruction count the lane-group mapping needs for 4.  What is left is the byte traffic:
 //   * state / actions / per-agent outputs: an env's A bytes are ONE 8-byte (A = 8) or 4-byte (A = 4)
 //     word per thread — consecutive threads, consecutive words: coalesced without staging;
-//   * observations: every thread writes its env's row template into shared memory (conflict-free
-//     16-byte stores), then the warp streams the 32 envs' rows (38.9 KB for A = 8, float32) to HBM as
-//     consecutive 16-byte vectors, each assembled from two template pairs through a per-CTA table
-//     of template offsets (the map is periodic in the env).
+//   * observations (float32): every thread writes its env's 2A+3-pair row template into shared memory
+//     (conflict-free 8-byte stores); then, env by env, the warp assembles the env's block of A rows in a
+//     shared-memory image — lane l gathers output pairs l, l+32, ... through a per-CTA table of
+//     template offsets — and one lane hands the image to the TMA unit (cp.async.bulk, SASS UBLKCP).
+//     Stores issued with st.global would stall the SM's load/store pipe, and with it every other
+//     warp's shared-memory work, whenever HBM pushes back (profiles/probes/lsu_coupling_probe.cu);
+//   * a launch may run n_steps > 1 steps per env with the state in registers (cc_rollout_fused).
 // Semantics, quirks and RNG streams are those of cc_kernels.cuh / oracle/cc_oracle.c; every block
 // cites the reference lines it restates (paths relative to /root/reference/src/collectivecrossing/).
 #pragma once
@@ -25,9 +28,6 @@
 #ifndef CCB_TPE_CONST_REGS
 #define CCB_TPE_CONST_REGS 0   // TMA gather: 1 = lanes whose pair is K1 / K2 / M keep it in a register (predicated load, no bank
                                // conflicts, 4 instructions per pair); 0 = every lane loads from the template (1 instruction, 2-way conflicts)
-#endif
-#ifndef CCB_TPE_STAGGER_NS
-#define CCB_TPE_STAGGER_NS 0
 #endif
 #ifndef CCB_TPE_DYNAMIC
 #define CCB_TPE_DYNAMIC 1      // warps take their next group of 32 envs from an atomic counter (no tail round, ascending writes)
@@ -334,11 +334,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     // atomic counter, fetched one iteration ahead so that the round trip is hidden.  Compared with a
     // fixed stride this has no partially filled last round, and the groups in flight stay a compact,
     // ascending window of the output (profiles/probes/store_pattern_probe.cu: 6.2 -> 6.9 TB/s).
-#if CCB_TPE_STAGGER_NS > 0
-    // de-phase the warps of an SM: all warps of a launch would otherwise step their first group together,
-    // then store together, and so on (the store phase is paced by HBM and re-synchronises them)
-    if (kHasObs) __nanosleep((unsigned)((warp & 3) * CCB_TPE_STAGGER_NS));
-#endif
+    // (De-phasing the warps of an SM at launch with a per-warp delay was measured: no effect.)
     // The record of a group: one word per byte row, step counter, return.  (Fetching it one group ahead,
     // before the previous group's rows are streamed out, was measured: no gain, 10 more live registers.)
     struct Record { uint2 x, y, fl; int step; float ep_ret; };

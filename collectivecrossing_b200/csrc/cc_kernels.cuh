@@ -15,9 +15,6 @@
 
 #include "../../include/ccb200.h"
 
-#ifndef CCB_PREFETCH
-#define CCB_PREFETCH 0   // software prefetch of the next group's record (measured: no gain)
-#endif
 #ifndef CCB_MIN_BLOCKS
 #define CCB_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must allow (A/B in DESIGN.md §6)
 #endif
@@ -434,8 +431,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
 
     const int total_warps = (int)gridDim.x * kWarpsPerCta;
     const int n_groups = (int)p.n_groups;
-    // The record of group g + total_warps is fetched while group g is processed (software prefetch:
-    // the loads at the top of an iteration were the largest single stall of the kernel).
+    // (Fetching the record of group g + total_warps while group g is processed was measured: no gain.)
     struct Record { unsigned x[APL], y[APL], fl[APL]; int act[APL]; int step; float ep_ret; };
     auto fetch = [&](int gg, Record &r) {
         const long long m0 = (long long)gg * EPW;
@@ -454,14 +450,8 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
         r.ep_ret = kMoves ? p.ep_ret[(int)m0 + tl] : 0.f;
     };
     Record next;
-    int g = (int)blockIdx.x * kWarpsPerCta + warp;
-#if CCB_PREFETCH
-    if (g < n_groups) fetch(g, next);
-#endif
-    for (; g < n_groups; g += total_warps) {
-#if !CCB_PREFETCH
+    for (int g = (int)blockIdx.x * kWarpsPerCta + warp; g < n_groups; g += total_warps) {
         fetch(g, next);
-#endif
         const long long n0 = (long long)g * EPW;
         const int envs_here = (int)min((long long)EPW, p.n_envs - n0);
         const bool env_ok = T.tile < envs_here;           // false only in the ragged last group
@@ -471,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
 #pragma unroll
         for (int k = 0; k < APL; ++k) off[k] = row0 + (env_ok ? aload[k] : aload[k] - T.tile * A);
 
-        // ---- the env's record (one contiguous run of bytes per array per warp), prefetched ----------
+        // ---- the env's record (one contiguous run of bytes per array per warp) ------------------------
         unsigned pos[APL];   // x << 8 | y (both 0..126 for every reachable state)
         unsigned fl[APL];
         int action[APL];
@@ -483,9 +473,6 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
         }
         int step = next.step;
         float ep_ret = next.ep_ret;
-#if CCB_PREFETCH
-        if (g + total_warps < n_groups) fetch(g + total_warps, next);
-#endif
 
         // table coordinates (clamped: set_state promises in-lattice positions; the clamp only keeps
         // shared-memory reads in bounds for garbage) and the padded-lattice cell of every owned agent
