@@ -271,8 +271,14 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     // lives in the warp's image ring, which is idle while the warp steps its envs (kBmStride = 32 lanes);
     // otherwise in its own region behind the templates (kBmStride = threads of the CTA).
     constexpr int kBmStride = L::kTma ? 32 : kTpeThreads;
-    unsigned *bm = L::kTma ? reinterpret_cast<unsigned *>(wstage + L::kTplBytesPerWarp) + lane
-                           : reinterpret_cast<unsigned *>(smem + L::kStageBytes) + threadIdx.x;
+    unsigned *bm_ptr = L::kTma ? reinterpret_cast<unsigned *>(wstage + L::kTplBytesPerWarp) + lane
+                               : reinterpret_cast<unsigned *>(smem + L::kStageBytes) + threadIdx.x;
+    // (accessed through its 32-bit shared-space address: the word index is data dependent, and generic 64-bit
+    // address arithmetic per access was a fifth of the policy's instructions)
+    const unsigned bm = (unsigned)__cvta_generic_to_shared(bm_ptr);
+    constexpr unsigned kBmWord = 4u * kBmStride;   // bytes between consecutive words of one thread
+    auto bm_load = [&](unsigned word) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(bm + word * kBmWord)); return v; };
+    auto bm_store = [&](unsigned word, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(bm + word * kBmWord), "r"(v) : "memory"); };
 
     // ---- once per CTA: tables (same contents as cc_kernels.cuh) -------------------------------------
     for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
@@ -437,14 +443,14 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
                 }
-                for (int w = 0; w < p.tpe_bm_words; ++w) bm[w * kBmStride] = ~walk[w];
+                for (int w = 0; w < p.tpe_bm_words; ++w) bm_store((unsigned)w, ~walk[w]);
 #pragma unroll
                 for (int k = 0; k < A; ++k)
-                    if (fl[k] & CC_F_ACTIVE) bm[(cell[k] >> 5) * kBmStride] |= 1u << (cell[k] & 31);
+                    if (fl[k] & CC_F_ACTIVE) bm_store((unsigned)cell[k] >> 5, bm_load((unsigned)cell[k] >> 5) | (1u << (cell[k] & 31)));
 #pragma unroll
                 for (int k = 0; k < A; ++k) {
                     const int c = cell[k];
-                    auto blocked = [&](int idx) { return (bm[(idx >> 5) * kBmStride] >> (idx & 31)) & 1u; };
+                    auto blocked = [&](int idx) { return (bm_load((unsigned)idx >> 5) >> (idx & 31)) & 1u; };
                     vmask[k] = (blocked(c + 1) | (blocked(c + PW) << 1) | (blocked(c - 1) << 2) | (blocked(c - PW) << 3)) ^ 15u;
                 }
             } else {

@@ -536,3 +536,35 @@ def test_fused_rollout_equals_repeated_steps(case, policy, obs_dtype):
     for e in envs:
         e.check_error()
         e.close()
+
+
+def test_fused_rollout_at_scale_equals_steps_and_keeps_invariants():
+    """BASELINE config 2 / 5 shape at 262,144 envs: one fused launch of 12 steps against 12 single-step
+    launches (every output tensor equal), then the reachable-state invariants on the result."""
+    cfg = readme_config(max_steps=30)
+    n, T = 1 << 18, 12
+    a = make_env(cfg, n, seed=21, obs_dtype="float32", auto_reset=True, with_info=True)
+    b = make_env(cfg, n, seed=21, obs_dtype="float32", auto_reset=True, with_info=True)
+    a.reset()
+    b.reset()
+    for _ in range(25):       # into the regime where episodes end and envs are re-placed inside the launch
+        a.step(policy="waiting")
+        b.step(policy="waiting")
+    traj = a.rollout_trajectory(T, policy="waiting")
+    resets = 0
+    for t in range(T):
+        out = b.step(policy="waiting")
+        resets += int(out.was_reset.sum())
+        assert torch.equal(traj["obs"][t], out.obs) and torch.equal(traj["reward"][t], out.reward), t
+        assert torch.equal(traj["agent_flags"][t], out.agent_flags) and torch.equal(traj["env_flags"][t], out.env_flags), t
+        assert torch.equal(traj["agent_info"][t], out.agent_info) and torch.equal(traj["actions"][t], out.actions), t
+    assert resets > 0
+    for name in ("x", "y", "flags", "step_count", "episode_return"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    _check_invariants(a, cfg, b.step(policy="waiting") if False else out)
+    sa, sb = a.stats(), b.stats()
+    for k in ("env_steps", "episodes", "terminated_all", "truncated_all", "arrivals", "episode_length_sum"):
+        assert sa[k] == sb[k], k
+    a.check_error()
+    a.close()
+    b.close()
