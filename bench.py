@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--obs-dtype", default="float32", choices=["float32", "int8", "none"])
     ap.add_argument("--policy", default="greedy", choices=["greedy", "waiting", "random"])
-    ap.add_argument("--steps-per-launch", type=int, default=16,
+    ap.add_argument("--steps-per-launch", type=int, default=20,
                     help="env-steps fused into one launch (cc_rollout_fused); 1 = one launch per step")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements")
