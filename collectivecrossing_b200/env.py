@@ -61,6 +61,17 @@ class CollectiveCrossingEnv(_Base):
         self._host = self._dev.make_host_buffers(pinned=False)
         self._host["order"] = torch.zeros((1, len(self._ids)), dtype=torch.int8)
         self._np_random: np.random.Generator | None = None  # only for user code that samples from it
+        # the reference's strategy objects (collectivecrossing.py:69-78); their values come from the device
+        from .observations import get_observation_function
+        from .rewards import get_reward_function
+        from .terminateds import get_terminated_function
+        from .truncateds import get_truncated_function
+
+        self._observation_function = get_observation_function(config.observation_config)
+        self._reward_function = get_reward_function(config.reward_config)
+        self._terminated_function = get_terminated_function(config.terminated_config)
+        self._truncated_function = get_truncated_function(config.truncated_config)
+        self._evaluators: dict = {}
         self._setup_spaces()
         super().__init__()
         self._agents_truncated_or_terminated_this_step: set[str] = set()
@@ -109,6 +120,9 @@ class CollectiveCrossingEnv(_Base):
 
     def close(self) -> None:
         self._dev.close()
+        for ev in self._evaluators.values():
+            ev.close()
+        self._evaluators = {}
 
     def render(self, mode: str | None = None):
         """``rgb_array`` image of the current host view (numpy rasteriser, ``rendering.py``); the
@@ -142,8 +156,9 @@ class CollectiveCrossingEnv(_Base):
             self.observation_space = self._observation_spaces[self._ids[0]]
 
     # ---- host view <-> device state ----------------------------------------------------------------
-    def _push_state(self) -> None:
+    def _push_state(self, dev: Any = None, step_offset: int = 0) -> None:
         """Upload the host records (tests and policies may have edited them) to the device."""
+        dev = dev or self._dev
         A = len(self._ids)
         x, y, f = np.zeros((1, A), np.int8), np.zeros((1, A), np.int8), np.zeros((1, A), np.uint8)
         for k, a in enumerate(self._ids):
@@ -152,8 +167,8 @@ class CollectiveCrossingEnv(_Base):
                 raise RuntimeError("call reset() before step()")
             x[0, k], y[0, k] = int(ag.position[0]), int(ag.position[1])
             f[0, k] = (_abi.F_ACTIVE if ag.active else 0) | (_abi.F_TERMINATED if ag.terminated else 0) | (_abi.F_TRUNCATED if ag.truncated else 0)
-        self._dev.set_state(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(f),
-                            torch.tensor([self._step_count], dtype=torch.int32))
+        dev.set_state(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(f),
+                      torch.tensor([self._step_count + step_offset], dtype=torch.int32))
 
     def _pull_state(self) -> None:
         x, y, f = self._dev.x.cpu().numpy()[0], self._dev.y.cpu().numpy()[0], self._dev.flags.cpu().numpy()[0]
@@ -235,6 +250,44 @@ class CollectiveCrossingEnv(_Base):
         terminateds["__all__"] = bool(ef & _abi.E_TERMINATED_ALL)
         truncateds["__all__"] = bool(ef & _abi.E_TRUNCATED_ALL)
         return observations, rewards, terminateds, truncateds, infos
+
+    # ---- strategy values of the current state (collectivecrossing.py:590-633) ----------------------
+    def _evaluate(self, reward_config: Any = None, terminated_config: Any = None, truncated_config: Any = None) -> dict:
+        """``{"rewards", "terminateds", "truncateds"}`` of the CURRENT host view, as the reference's
+        ``calculate_reward / calculate_terminated / calculate_truncated`` return them for every agent
+        (absent key = ``None``).  Computed by the step kernel: a scratch one-env handle with the (possibly
+        overridden) strategy configs takes ONE step with WAIT actions from this state at step count - 1,
+        which evaluates exactly these functions on unchanged positions (collectivecrossing.py:204-241)."""
+        key = (repr(reward_config), repr(terminated_config), repr(truncated_config))
+        ev = self._evaluators.get(key)
+        if ev is None:
+            upd = {k: v for k, v in (("reward_config", reward_config), ("terminated_config", terminated_config),
+                                     ("truncated_config", truncated_config)) if v is not None}
+            cfg = self._config.model_copy(update=upd) if upd else self._config
+            ev = self._evaluators[key] = BatchedCollectiveCrossing(cfg, 1, self._dev.device, obs_dtype="none", reward_dtype="float64",
+                                                                   auto_reset=False)
+        self._push_state(ev, step_offset=-1)
+        wait = torch.full((1, len(self._ids)), 4, dtype=torch.int8, device=ev.device)
+        out = ev.step(wait)
+        ev.check_error()
+        rew, af = out.reward.cpu().numpy()[0], out.agent_flags.cpu().numpy()[0]
+        res: dict = {"rewards": {}, "terminateds": {}, "truncateds": {}}
+        for k, a in enumerate(self._ids):
+            bits = int(af[k])
+            res["terminateds"][a] = bool(bits & _abi.O_TERM_VALUE)
+            if bits & _abi.O_ALIVE_PREV:
+                res["rewards"][a] = float(rew[k])
+                res["truncateds"][a] = bool(bits & _abi.O_TRUNC_VALUE)
+        return res
+
+    def _calculate_reward(self, agent_id: str) -> float | None:
+        return self._reward_function.calculate_reward(agent_id, self)
+
+    def _calculate_terminated(self, agent_id: str) -> bool | None:
+        return self._terminated_function.calculate_terminated(agent_id, self)
+
+    def _calculate_truncated(self, agent_id: str) -> bool | None:
+        return self._truncated_function.calculate_truncated(agent_id, self)
 
     # ---- predicates and accessors used by tests and the baseline policies ---------------------------
     def _get_agent(self, agent_id: str) -> Agent:

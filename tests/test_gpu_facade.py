@@ -200,3 +200,121 @@ def test_env_config_dict_like_rllib():
     obs, _ = env.reset(seed=42)
     assert [int(obs[a][0]) for a in env.possible_agents] == [1, 7, 5, 1, 2, 6, 8, 9]  # SURVEY.md §8c known answer
     env.close()
+
+
+# ---- the strategy objects (the reference's plugin API), evaluated on the device --------------------------
+def _inject(env, ref, rng):
+    """Same random valid state into the facade's host records and the pure-Python port."""
+    cfg = env.config
+    cells = [(x, y) for x in range(cfg.width + 1) for y in range(cfg.height + 1) if ref.valid(x, y)]
+    picks = rng.choice(len(cells), size=len(ref.ids), replace=False)
+    for a, k in zip(ref.ids, picks):
+        x, y = cells[k]
+        ref.pos[a], ref.active[a], ref.term[a], ref.trunc[a] = (x, y), True, False, False
+        ag = env._agents[a]
+        ag.position, ag.active, ag.terminated, ag.truncated = np.array([x, y]), True, False, False
+
+
+@pytest.mark.parametrize("reward", ["default", "simple_distance", "binary", "constant_negative"])
+def test_reward_function_objects_match_python_port(reward):
+    """rewards.py:41-182 through ``env._reward_function.calculate_reward`` / ``env._calculate_reward`` on random
+    valid states, and through function objects of the OTHER kinds built from their own configs
+    (test_rewards.py:34-160: exact constants for binary / constant_negative)."""
+    from oracle.pyport import PyEnv
+
+    from collectivecrossing_b200.rewards import REWARD_FUNCTIONS, get_reward_function
+
+    cfg = readme_config(reward)
+    env, ref = make(cfg), PyEnv(cfg)
+    env.reset(seed=1)
+    ref.reset(seed=1)
+    assert type(env._reward_function) is REWARD_FUNCTIONS[reward]
+    rng = np.random.default_rng(3)
+    for _ in range(12):
+        _inject(env, ref, rng)
+        for a in ref.ids:
+            want = float(ref.reward(a))
+            got = env._calculate_reward(a)
+            assert isinstance(got, float) and got == want, (a, got, want)
+            assert env._reward_function.calculate_reward(a, env) == want
+    # a function object evaluates with ITS config, whatever the env was built with
+    other = readme_config("constant_negative", step_penalty=-2.5)
+    fn = get_reward_function(other.reward_config)
+    assert all(fn.calculate_reward(a, env) == -2.5 for a in ref.ids)
+    # rewards.py:65-66: None for agents that are terminated or truncated (test_rewards.py:222-327, 476-526)
+    env._agents["boarding_0"].terminated = True
+    env._agents["exiting_0"].truncated = True
+    assert env._calculate_reward("boarding_0") is None and env._calculate_reward("exiting_0") is None
+    assert env._calculate_reward("boarding_1") is not None
+    env.close()
+
+
+@pytest.mark.parametrize("current_step,max_steps,expected", [(0, 10, False), (5, 10, False), (9, 10, False), (10, 10, True),
+                                                             (11, 10, True), (0, 1, False), (1, 1, True), (999, 1000, False), (1000, 1000, True)])
+def test_truncated_function_truth_table(current_step, max_steps, expected):
+    """test_truncateds.py:14-53: ``calculate_truncated`` is ``step_count >= max_steps``; None for a done agent."""
+    from collectivecrossing_b200.truncateds import MaxStepsTruncatedFunction
+
+    env = make(readme_config(max_steps=max_steps))
+    env.reset(seed=42)
+    assert isinstance(env._truncated_function, MaxStepsTruncatedFunction)
+    env._step_count = current_step
+    for a in env.possible_agents:
+        assert env._truncated_function.calculate_truncated(a, env) is expected
+        assert env._calculate_truncated(a) is expected
+    env._agents["boarding_0"].terminated = True
+    assert env._calculate_truncated("boarding_0") is None
+    env.close()
+
+
+@pytest.mark.parametrize("term", ["individual", "all"])
+def test_terminated_function_objects(term):
+    """test_terminateds.py:29-133: nobody is terminated after reset; an agent moved to its destination row is
+    terminated in the individual mode at once, in the all-at-destination mode only when everybody is there."""
+    from collectivecrossing_b200.terminateds import TERMINATED_FUNCTIONS
+
+    cfg = readme_config(term=term)
+    env = make(cfg)
+    env.reset(seed=42)
+    name = {"individual": "individual_at_destination", "all": "all_at_destination"}[term]
+    assert type(env._terminated_function) is TERMINATED_FUNCTIONS[name]
+    assert not any(env._calculate_terminated(a) for a in env.possible_agents)
+    env._agents["boarding_0"].position = np.array([5, cfg.boarding_destination_area_y])
+    assert env._calculate_terminated("boarding_0") is (term == "individual")
+    assert env._calculate_terminated("exiting_0") is False
+    for k, a in enumerate(env.possible_agents):      # everybody onto the destination row (distinct x)
+        y = cfg.boarding_destination_area_y if a.startswith("boarding") else cfg.exiting_destination_area_y
+        env._agents[a].position = np.array([3 + k if a.startswith("boarding") else k, y])
+    assert all(env._calculate_terminated(a) is True for a in env.possible_agents)
+    env.close()
+
+
+def test_observation_function_integration_and_registries():
+    """test_collective_crossing.py:260-277, 396-429: the observation function object returns what reset / step
+    returned; unknown names raise with the reference's message."""
+    from collectivecrossing_b200.observations import DefaultObservationFunction, get_observation_function
+    from collectivecrossing_b200.rewards import get_reward_function
+
+    env = make(readme_config())
+    obs, _ = env.reset(seed=42)
+    assert isinstance(env._observation_function, DefaultObservationFunction)
+    assert env._observation_function.observation_config.get_observation_function_name() == "default"
+    for a in env.possible_agents:
+        assert np.array_equal(obs[a], env._observation_function.get_agent_observation(a, env))
+        assert env._observation_function.return_agent_observation_space(a, env).shape == (38,)
+    obs, *_ = env.step({a: 4 for a in env.possible_agents})
+    for a in obs:
+        assert np.array_equal(obs[a], env._observation_function.get_agent_observation(a, env))
+
+    class Invalid:
+        def get_observation_function_name(self):
+            return "invalid"
+
+        def get_reward_function_name(self):
+            return "invalid"
+
+    with pytest.raises(ValueError, match="Unknown observation function 'invalid'"):
+        get_observation_function(Invalid())
+    with pytest.raises(ValueError, match="Unknown reward function 'invalid'"):
+        get_reward_function(Invalid())
+    env.close()
