@@ -33,4 +33,11 @@ def __getattr__(name):
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
+try:  # the reference registers its env with gymnasium at import (collectivecrossing/__init__.py:3-10)
+    from gymnasium.envs.registration import register as _register  # type: ignore
+
+    _register(id="collectivecrossing_b200/CollectiveCrossing-v0", entry_point="collectivecrossing_b200.env:CollectiveCrossingEnv")
+except Exception:  # gymnasium is not part of this stack: nothing to register with
+    pass
+
 __all__ = ["CollectiveCrossingConfig", *_LAZY]
