@@ -161,6 +161,27 @@ int main() {
     run<1216, 2, false, 7 + 32>(out, counter, sink, sms, 3, 0, small);
     run<1216, 2, false, 6>(out, counter, sink, sms, 3, 0, small);
     run<1216, 2, false, 6 + 32>(out, counter, sink, sms, 3, 0, small);
+    for (size_t carve_mb : {36, 48, 64}) {
+        // persisting L2 carve-out sized for the state arrays only (first 32 MB of `small`), normal policy for everything else
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve_mb << 20);
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.base_ptr = small;
+        attr.accessPolicyWindow.num_bytes = (size_t)32 << 20;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        cudaError_t e = cudaStreamSetAttribute(0, cudaStreamAttributeAccessPolicyWindow, &attr);
+        printf("state window 32 MB persisting, carve-out %zu MB: %s\n", carve_mb, cudaGetErrorString(e));
+        run<1216, 2, false, 3>(out, counter, sink, sms, 3, 0, small);
+        run<1216, 2, false, 7>(out, counter, sink, sms, 3, 0, small);
+        run<1216, 2, false, 7 + 16>(out, counter, sink, sms, 3, 0, small);
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(0, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
+    }
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    run<1216, 2, false, 7>(out, counter, sink, sms, 3, 0, small);
+    return 0;
     run<1216, 2, false, 128>(out, counter, sink, sms, 3, 0, small);
     run<1216, 2, false, 128 + 16>(out, counter, sink, sms, 3, 0, small);
     run<1216, 2, true, 128 + 16>(out, counter, sink, sms, 3, 100, small);
