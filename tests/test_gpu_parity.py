@@ -568,3 +568,33 @@ def test_fused_rollout_at_scale_equals_steps_and_keeps_invariants():
     a.check_error()
     a.close()
     b.close()
+
+
+def test_envs_at_high_indices_equal_single_env_handles():
+    """BASELINE config 5 scale on one GPU (4,194,304 envs): the RNG is keyed on the global env index, so env k of
+    the big batch must follow exactly the trajectory of a one-env handle created with global_env_offset = k —
+    checked at the first, middle and last indices, through single-step and fused launches."""
+    cfg = readme_config(max_steps=20)
+    n = 1 << 22
+    big = make_env(cfg, n, seed=5, obs_dtype="float32", auto_reset=True)
+    big.reset()
+    ks = [0, 12345, n // 2 + 7, n - 33, n - 1]
+    smalls = [make_env(cfg, 1, seed=5, global_env_offset=k, obs_dtype="float32", auto_reset=True) for k in ks]
+    for s in smalls:
+        s.reset()
+    for t in range(26):
+        out = big.step(policy="waiting")
+        for k, s in zip(ks, smalls):
+            o = s.step(policy="waiting")
+            assert torch.equal(out.obs[k], o.obs[0]) and torch.equal(out.reward[k], o.reward[0]), (t, k)
+            assert torch.equal(big.x[k], s.x[0]) and int(out.env_flags[k]) == int(o.env_flags[0]), (t, k)
+    traj = big.rollout_trajectory(4, policy="waiting")
+    for k, s in zip(ks, smalls):
+        for t in range(4):
+            o = s.step(policy="waiting")
+            assert torch.equal(traj["obs"][t][k], o.obs[0]) and torch.equal(traj["reward"][t][k], o.reward[0]), (t, k)
+    big.check_error()
+    assert big.stats()["env_steps"] == 30 * n
+    big.close()
+    for s in smalls:
+        s.close()
