@@ -469,6 +469,34 @@ def secondary(args, torch, dist, cfg):
         env.close()
         del env
         torch.cuda.empty_cache()
+    # the host-buffer path with the compact int8 observation rows (4x less PCIe traffic than the reference's float32 rows;
+    # a consumer that needs float32 widens them on its side) — reported beside the float32 `e2e`, never instead of it
+    env = BatchedCollectiveCrossing(cfg, M, dev, seed=1, obs_dtype="int8", auto_reset=True)
+    env.reset()
+    host = env.make_host_buffers(pinned=True)
+    dev_actions = torch.zeros((M, env.num_agents), dtype=torch.int8, device=dev)
+
+    def e2e_step():
+        env.policy_actions("greedy", out=dev_actions)
+        host["actions"].copy_(dev_actions, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        env.step_host(host)
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(12):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["e2e_host_buffers_int8_obs_1M_envs"] = {"agent_steps_per_sec": M * env.num_agents * 12 / dt, "ms_per_step": dt / 12 * 1e3,
+                                                "d2h_bytes_per_step": M * env.num_agents * (env.obs_len + 4 + 3) + M, "kernel": env.last_kernel,
+                                                "algorithmic_GBps": 0.0, "agents_per_env": env.num_agents, "envs": M}
+    env.close()
+    del env, host
+    torch.cuda.empty_cache()
+
     # fused multi-step launches (cc_rollout_fused): T env-steps per env per launch, the state stays in registers;
     # every step's observations, rewards and flags are still written ([T, N, ...] buffers).  Algorithmic bytes per
     # env-step: the state term 2(3A+4)+8 of SURVEY.md 8d is paid once per T steps.
