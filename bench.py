@@ -500,8 +500,8 @@ def secondary(args, torch, dist, cfg):
     # fused multi-step launches (cc_rollout_fused): T env-steps per env per launch, the state stays in registers;
     # every step's observations, rewards and flags are still written ([T, N, ...] buffers).  Algorithmic bytes per
     # env-step: the state term 2(3A+4)+8 of SURVEY.md 8d is paid once per T steps.
-    for T in (4, 16):
-        env = BatchedCollectiveCrossing(cfg, M, dev, seed=1, obs_dtype="float32", auto_reset=True)
+    for T, n_envs in ((4, M), (16, M), (20, 65536)):
+        env = BatchedCollectiveCrossing(cfg, n_envs, dev, seed=1, obs_dtype="float32", auto_reset=True)
         env.reset()
         env.rollout_trajectory(T, policy="greedy")
         launches = 12
@@ -516,9 +516,9 @@ def secondary(args, torch, dist, cfg):
         env.check_error()
         a = env.num_agents
         bytes_step = a + (2 * (3 * a + 4) + 8) / T + 5 * a + 1 + 4 * a * (6 + 4 * a)
-        out[f"fused_rollout_T{T}_1M_envs_fp32_greedy"] = {
-            "agent_steps_per_sec": M * a / (ms * 1e-3), "ms_per_step": ms, "algorithmic_GBps": bytes_step * M / (ms * 1e-3) / 1e9,
-            "algorithmic_bytes_per_env_step": bytes_step, "kernel": env.last_kernel, "agents_per_env": a, "envs": M, "steps_per_launch": T}
+        out[f"fused_rollout_T{T}_{'1M' if n_envs == M else n_envs}_envs_fp32_greedy"] = {
+            "agent_steps_per_sec": n_envs * a / (ms * 1e-3), "ms_per_step": ms, "algorithmic_GBps": bytes_step * n_envs / (ms * 1e-3) / 1e9,
+            "algorithmic_bytes_per_env_step": bytes_step, "kernel": env.last_kernel, "agents_per_env": a, "envs": n_envs, "steps_per_launch": T}
         env.close()
         del env
         torch.cuda.empty_cache()
