@@ -35,6 +35,15 @@ def readme_config(reward="default", term="individual", max_steps=100, **reward_k
     )
 
 
+def readme_crew(boarding, exiting, reward="default", term="individual", max_steps=40):
+    """The README geometry (small lattice: the policies use per-thread bitmaps) with another crew."""
+    return CollectiveCrossingConfig(
+        width=12, height=8, division_y=4, tram_door_left=5, tram_door_right=7, tram_length=9,
+        num_boarding_agents=boarding, num_exiting_agents=exiting, exiting_destination_area_y=0, boarding_destination_area_y=8,
+        reward_config=REWARDS[reward](), terminated_config=TERMS[term](), truncated_config=MaxStepsTruncatedConfig(max_steps=max_steps),
+    )
+
+
 def cassette_config():
     """The env of the reference's golden cassettes (tests/.../test_trajectory_vcr.py:323-340)."""
     return CollectiveCrossingConfig(

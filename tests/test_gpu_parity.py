@@ -4,7 +4,7 @@ rewards in float64 and rounds once — also for float32/float64 rewards."""
 
 import numpy as np
 import pytest
-from cases import GOLDEN_CASES, cassette_config, crew_config, large_config, readme_config
+from cases import GOLDEN_CASES, cassette_config, crew_config, large_config, readme_config, readme_crew
 from helpers import CASSETTE_BITS, assert_same, load_golden, random_states, replay_device
 
 from collectivecrossing_b200 import _abi
@@ -79,6 +79,9 @@ ORACLE_CASES = {
     "A5": (lambda: crew_config(3, 2, max_steps=40, term="all"), 258),
     "A6": (lambda: crew_config(4, 2, max_steps=40), 131),
     "A7": (lambda: crew_config(4, 3, max_steps=40, reward="constant_negative", term="all"), 260),
+    "A4_small_lattice": (lambda: readme_crew(2, 2, term="all"), 333),
+    "A6_small_lattice": (lambda: readme_crew(4, 2, reward="simple_distance"), 300),
+    "A7_small_lattice": (lambda: readme_crew(4, 3), 129),
     "A8_readme": (lambda: readme_config(max_steps=60), 1031),
     "A12": (lambda: crew_config(7, 5, max_steps=40, reward="simple_distance"), 130),
     "A21_odd": (lambda: crew_config(13, 8, max_steps=40), 67),
@@ -101,7 +104,7 @@ def _compare_step(env, orc, res, out, tag, obs_np):
 
 
 # every case with the default mapping, and the crews the thread-per-env kernel takes also with the lane-group one
-SMALL_CREWS = ("A1", "A2", "A3_cassette", "A4", "A5", "A6", "A7", "A8_readme")   # served by the thread-per-env kernel
+SMALL_CREWS = ("A1", "A2", "A3_cassette", "A4", "A5", "A6", "A7", "A4_small_lattice", "A6_small_lattice", "A7_small_lattice", "A8_readme")   # served by the thread-per-env kernel
 CASE_KERNELS = [(c, "auto") for c in ORACLE_CASES] + [(c, "lanes") for c in SMALL_CREWS]
 
 
