@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
         if (MODE == kModePolicy) {
 #pragma unroll
             for (int k = 0; k < APL; ++k)
-                if (env_ok && avalid[k]) p.actions_out[off[k]] = (int8_t)action[k];
+                if (env_ok && avalid[k]) __stcs(reinterpret_cast<signed char *>(p.actions_out) + off[k], (signed char)action[k]);
             continue;
         }
 
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             if (p.actions_out) {
 #pragma unroll
                 for (int k = 0; k < APL; ++k)
-                    if (env_ok && avalid[k]) p.actions_out[off[k]] = (int8_t)action[k];
+                    if (env_ok && avalid[k]) __stcs(reinterpret_cast<signed char *>(p.actions_out) + off[k], (signed char)action[k]);
             }
             // ---- collectivecrossing.py:188 ---------------------------------------------------
             step += 1;
@@ -704,11 +704,13 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
                             default: r = p.rp[0]; break;
                             }
                         }
-                        reinterpret_cast<double *>(p.reward)[off[k]] = r;
-                    } else reinterpret_cast<float *>(p.reward)[off[k]] = rew[k];
-                    p.agent_flags[off[k]] = (uint8_t)oflag[k];
+                        __stcs(reinterpret_cast<double *>(p.reward) + off[k], r);
+                    } else __stcs(reinterpret_cast<float *>(p.reward) + off[k], rew[k]);
+                    // (per-step outputs are written once and never read by the kernels: streaming stores keep them from
+                    // displacing the state in L2 — measured on the thread-per-env kernel: 0.2545 -> 0.2422 ms per launch)
+                    __stcs(reinterpret_cast<unsigned char *>(p.agent_flags) + off[k], (unsigned char)oflag[k]);
                     // :248-254: in_tram_area | at_door | active | at_destination
-                    if (p.agent_info) p.agent_info[off[k]] = (uint8_t)((geo_f[k] & 0xBu) | ((fl[k] & 1u) << 2));
+                    if (p.agent_info) __stcs(reinterpret_cast<unsigned char *>(p.agent_info) + off[k], (unsigned char)((geo_f[k] & 0xBu) | ((fl[k] & 1u) << 2)));
                 }
             const bool leader = env_ok && T.li == 0;
             if (leader) st_rsum += (double)rsum;
@@ -818,7 +820,7 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
             if (wr && T.li == 0) {
                 p.step[(int)n0 + T.tile] = step;
                 p.ep_ret[(int)n0 + T.tile] = ep_ret;
-                if (MODE == kModeStep) p.env_flags[(int)n0 + T.tile] = (uint8_t)eflags;
+                if (MODE == kModeStep) __stcs(reinterpret_cast<unsigned char *>(p.env_flags) + (int)n0 + T.tile, (unsigned char)eflags);
             }
         }
 
