@@ -59,9 +59,10 @@ def config_dict(args, n_total):
                     f"IndividualAtDestination, MaxSteps 100, {args.policy} baseline policy in-kernel, auto-reset; "
                     f"{args.envs} envs per GPU",
         "envs_total": n_total, "envs_per_gpu": args.envs, "agents_per_env": 8, "obs_dtype": args.obs_dtype,
-        "policy": args.policy, "steps_per_launch": args.steps_per_launch,
-        "launch": (f"cc_rollout_fused: {args.steps_per_launch} env-steps per launch, state in registers, every step's outputs written "
-                   f"([T, N, ...] buffers); steps % T as single-step launches" if args.steps_per_launch > 1 else "cc_step: one launch per env-step"),
+        "policy": args.policy, "steps_per_launch_max": args.steps_per_launch,
+        "launch": (f"cc_rollout_fused: up to {args.steps_per_launch} env-steps per launch (see roofline.steps_per_launch), state in registers, "
+                   f"every step's outputs written ([T, N, ...] buffers); steps % T as single-step launches"
+                   if args.steps_per_launch > 1 else "cc_step: one launch per env-step"),
         "l2_policy": "inputs larger than L2 (no flush)" if args.envs >= 1 << 19 else "working set may fit L2",
         "parallelism": "independent env shards, one process per GPU, no data-path collective",
     }
@@ -318,7 +319,11 @@ def run_ours(args):
     env = sharded.env
     assert sharded.count == n and sharded.offset == rank * n
     env.reset()
+    # steps per fused launch: at most --steps-per-launch, chosen so that the K timed steps are (almost) whole launches
     T = max(1, args.steps_per_launch)
+    if T > 1:
+        n_launch = max(1, -(-args.steps // T))
+        T = max(1, args.steps // n_launch)
     for _ in range(args.warmup):
         env.step(policy=args.policy)
     if T > 1:
