@@ -363,7 +363,10 @@ def run_ours(args):
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get(f"{args.obs_dtype}_{args.policy}_{n}_T{T}")
+            table = json.loads(tp.read_text())
+            traffic = table.get(f"{args.obs_dtype}_{args.policy}_{n}_T{T}")
+            if traffic is None and T > 1 and f"{args.obs_dtype}_{args.policy}_{n}_T20" in table:
+                traffic = int(table[f"{args.obs_dtype}_{args.policy}_{n}_T20"] * T / 20)   # same kernel, same traffic per step
         except Exception:
             traffic = None
     kernel_name = ("ccb::cc_step_tpe_kernel<8,%s>" if env.last_kernel == "threads" else "ccb::cc_kernel<8,1,%s,step>") % {"float32": 4, "int8": 1, "none": 0}[args.obs_dtype]
