@@ -6,6 +6,10 @@
 #include <new>
 
 #include "cc_kernel_tpe.cuh"
+
+#ifndef CCB_TPE_ALTERNATE
+#define CCB_TPE_ALTERNATE 1   // single-step launches of the thread-per-env kernel alternate the direction in which groups are handed out
+#endif
 #include "cc_kernels.cuh"
 
 namespace {
@@ -179,6 +183,7 @@ int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
     p.slice_agents = (long long)h->n_envs * h->A;
     p.slice_envs = h->n_envs;
     p.slice_obs_bytes = OBS == CC_OBS_NONE ? 0 : (long long)h->n_envs * h->A * (6 + 4 * h->A) * (long long)OBS;
+    p.tpe_reverse = CCB_TPE_ALTERNATE && p.n_steps == 1 ? (int)(h->tpe_launches & 1) : 0;
     p.tpe_counter = h->tpe_counters + (h->tpe_launches & 1);
     p.tpe_counter_next = h->tpe_counters + ((h->tpe_launches + 1) & 1);
     // (with TMA rows the bitmap aliases the warp's image ring)
@@ -254,6 +259,7 @@ int step_on(cc_handle *h, const cc_step_io *io, cudaStream_t s, int n_steps = 1,
         return fail(CC_ERR_UNSUPPORTED, "CC_KERNEL_THREADS was requested but this step is not eligible (needs at most 8 agents, agent order, "
                                         "float32 rewards, int8 rows only for 8 agents, word-aligned rows for 4 or 8 agents)");
     const bool use_tpe = can_tpe && h->variant != CC_KERNEL_LANES;
+    if (!use_tpe) p.tpe_reverse = CCB_TPE_ALTERNATE ? (int)(h->t & 1) : 0;
     int rc = use_tpe ? launch_tpe(h, p, io->obs_dtype, s) : launch<ccb::kModeStep>(h, p, io->obs_dtype, s);
     if (n_steps > 1 && !use_tpe) return fail(CC_ERR_UNSUPPORTED, "fused multi-step launches need the thread-per-env kernel");
     if (rc == CC_OK) { h->t += (uint64_t)n_steps; h->last_variant = use_tpe ? CC_KERNEL_THREADS : CC_KERNEL_LANES; }

@@ -374,15 +374,19 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         r.step = CCB_TPE_STATE_STREAM == 1 ? __ldcs(p.step + nl) : p.step[nl];
         r.ep_ret = CCB_TPE_STATE_STREAM == 1 ? __ldcs(p.ep_ret + nl) : p.ep_ret[nl];
     };
-    int g = (int)blockIdx.x * kTpeWarps + warp;
+    // Work items are handed out in ascending order; with tpe_reverse (every other single-step launch) item w is
+    // group n_groups-1-w, so a launch starts on the groups the previous launch wrote LAST — the part of the
+    // state that is still in L2.
+    int gw = (int)blockIdx.x * kTpeWarps + warp;
     int g_next = 0;
     Record rec;
-    for (; g < n_groups; g = g_next) {
+    for (; gw < n_groups; gw = g_next) {
+        const int g = p.tpe_reverse ? n_groups - 1 - gw : gw;
         fetch(g, rec);
 #if CCB_TPE_DYNAMIC
         if (lane == 0) g_next = total_warps + (int)atomicAdd(p.tpe_counter, 1u);
 #else
-        g_next = g + total_warps;
+        g_next = gw + total_warps;
 #endif
         const int n = g * 32 + lane;
         const int envs_here = (int)min(32ll, p.n_envs - (long long)g * 32);

@@ -67,6 +67,7 @@ struct KParams {
     int smem_total;
     int tpe_bm_words;    // thread-per-env kernel: words of the private lattice bitmap (0 = compare-based occupancy)
     unsigned *tpe_counter, *tpe_counter_next;   // thread-per-env kernel: work counters of this / the next launch
+    int tpe_reverse;              // step kernels: process the groups from the last to the first (alternates between launches)
     // thread-per-env kernel, fused multi-step launches (cc_rollout_fused): every output is time-major [n_steps][...]
     // lane-group kernel, int8 rows of one-env-per-warp crews (A > 16) whose env block is a whole number of 16-byte
     // vectors: 8 copies of the row template, shifted by 0, 2, ..., 14 bytes, so that most output vectors are ONE
@@ -450,7 +451,10 @@ __global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CC
         r.ep_ret = kMoves ? p.ep_ret[(int)m0 + tl] : 0.f;
     };
     Record next;
-    for (int g = (int)blockIdx.x * kWarpsPerCta + warp; g < n_groups; g += total_warps) {
+    // (step launches alternate the direction: a launch starts on the groups the previous one wrote last, whose state is
+    // still in L2)
+    for (int gw = (int)blockIdx.x * kWarpsPerCta + warp; gw < n_groups; gw += total_warps) {
+        const int g = (MODE == kModeStep && p.tpe_reverse) ? n_groups - 1 - gw : gw;
         fetch(g, next);
         const long long n0 = (long long)g * EPW;
         const int envs_here = (int)min((long long)EPW, p.n_envs - n0);
