@@ -457,11 +457,11 @@ def secondary(args, torch, dist, cfg):
         ("1M_envs_fp32_waiting", cfg, M, "float32", "waiting", "auto", 50),
         ("1M_envs_fp32_random", cfg, M, "float32", "random", "auto", 50),
         ("1M_envs_fp32_greedy_lane_group_kernel", cfg, M, "float32", "greedy", "lanes", 50),
-        ("cfg3_64x32_64agents_simple_distance_all_1M_envs_int8_random", large_config(512), M, "int8", "random", "auto", 5),
-        ("cfg3_64x32_64agents_simple_distance_all_1M_envs_fp32_random", large_config(512), M, "float32", "random", "auto", 3),
         ("cfg4_binary_individual_4M_envs_fp32_random", readme_config("binary", "individual", 100, goal_reward=1.0, no_goal_reward=0.0), 4 * M, "float32", "random", "auto", 10),
         ("cfg4_constant_negative_individual_4M_envs_fp32_random", readme_config("constant_negative", "individual", 100, step_penalty=-1.0), 4 * M, "float32", "random", "auto", 10),
         ("cfg5_shard_2M_envs_fp32_waiting", cfg, 2 * M, "float32", "waiting", "auto", 20),
+        ("cfg3_64x32_64agents_simple_distance_all_1M_envs_int8_random", large_config(512), M, "int8", "random", "auto", 5),
+        ("cfg3_64x32_64agents_simple_distance_all_1M_envs_fp32_random", large_config(512), M, "float32", "random", "auto", 3),
     )
     for tag, c, n, obs, pol, kern, steps in runs:
         env = BatchedCollectiveCrossing(c, n, dev, seed=1, obs_dtype=obs, auto_reset=True, kernel=kern)
