@@ -601,3 +601,29 @@ def test_envs_at_high_indices_equal_single_env_handles():
     big.close()
     for s in smalls:
         s.close()
+
+
+@pytest.mark.parametrize("name", ["readme_greedy", "readme_waiting", "readme_binary_all", "readme_simple_all"])
+def test_fused_rollout_replays_reference_policy_recordings(name):
+    """The reference's own rollouts (env + GreedyPolicy / WaitingPolicy at epsilon 0, recorded by
+    tests/golden/make_golden.py) against ONE fused launch of all their steps: every step's positions are implied by
+    the observations, so observations, flags, infos, policy actions are compared bit for bit and rewards as the
+    correctly rounded float32 of the reference's float64."""
+    cfg, kw = GOLDEN_CASES[name][0](), GOLDEN_CASES[name][1]
+    rec = load_golden(name)
+    T, N, A = rec["actions"].shape
+    env = make_env(cfg, N, obs_dtype="float32", reward_dtype="float32", auto_reset=False, with_info=True)
+    env.set_state(*(torch.from_numpy(rec[k]).cuda() for k in ("init_x", "init_y", "init_flags", "init_step")))
+    traj = env.rollout_trajectory(T, policy=kw["source"])
+    assert env.last_kernel == "threads" and env.launch_count == 1
+    env.check_error()
+    got = {"reward": traj["reward"].cpu().numpy().astype(np.float64), "agent_flags": traj["agent_flags"].cpu().numpy(),
+           "agent_info": traj["agent_info"].cpu().numpy(), "env_flags": traj["env_flags"].cpu().numpy(),
+           "obs": traj["obs"].cpu().numpy().astype(np.int8), "actions": traj["actions"].cpu().numpy(),
+           "init_obs": rec["init_obs"]}
+    slim = {k: v for k, v in rec.items() if k not in ("x", "y", "flags", "step")}   # per-step state is not kept by a fused launch
+    assert_same(slim, got, f"fused/{name}", policy_actions=True, reward_rtol=1e-6)
+    assert np.array_equal(got["reward"], rec["reward"].astype(np.float32).astype(np.float64))
+    assert np.array_equal(env.x.cpu().numpy(), rec["x"][-1]) and np.array_equal(env.flags.cpu().numpy(), rec["flags"][-1])
+    assert np.array_equal(env.step_count.cpu().numpy(), rec["step"][-1])
+    env.close()
