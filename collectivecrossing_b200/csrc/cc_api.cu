@@ -177,6 +177,8 @@ int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
     const int bm_cap = L::kTma ? (L::kImgRing * L::kImgBytes / 128 < ccb::kTpeMaxBitmapWords ? L::kImgRing * L::kImgBytes / 128 : ccb::kTpeMaxBitmapWords)
                                : ccb::kTpeMaxBitmapWords;
     p.tpe_bm_words = (on_device_policy && p.walk_words <= bm_cap) ? p.walk_words : 0;
+    // one word per lattice row where the padded lattice has at most 32 columns and its rows fit the bitmap (README: 11 rows)
+    if (on_device_policy && p.W + 3 <= 32 && p.H + 3 <= bm_cap) { p.tpe_bm_words = p.H + 3; p.tpe_bm_rows = 1; }
     // launch k counts its groups in counter k & 1 and zeroes the other one for launch k + 1 (launches of
     // one handle are stream-ordered by contract)
     if (p.n_steps < 1) p.n_steps = 1;

@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PW = p.W + 3, PH = p.H + 3;  // lattice padded by one ring: x in [-1, W+1] -> column x+1
     __shared__ unsigned xt[kMaxPad], yt[2 * kMaxPad], walk[kMaxWalkWords];
+    __shared__ unsigned walk_row[kTpeMaxBitmapWords];   // row y of the padded lattice as one word (lattices up to 32 columns)
     __shared__ float rtab[kRtabSize];   // value for a boarding agent; exiting agents of the default reward get the negative
     __shared__ uint8_t act_tab[kPolicyRows * 16];
     __shared__ unsigned long long red_all[kTpeWarps * kStCount];
@@ -322,6 +323,11 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         const int idx = w * 32 + lane, yy = idx / PW - 1, xx = idx - (yy + 1) * PW - 1;
         const unsigned bits = __ballot_sync(kFull, valid_position(p, xx, yy));
         if (lane == 0) walk[w] = bits;
+    }
+    if (p.tpe_bm_rows && threadIdx.x < PH) {
+        unsigned bits = 0;
+        for (int c = 0; c < PW; ++c) bits |= valid_position(p, c - 1, (int)threadIdx.x - 1) ? (1u << c) : 0u;
+        walk_row[threadIdx.x] = bits;
     }
     if (kHasObs) {
         for (int w = threadIdx.x; w < L::kLutWords; w += blockDim.x) {
@@ -468,15 +474,34 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
                 }
-                for (int w = 0; w < p.tpe_bm_words; ++w) bm_store((unsigned)w, ~walk[w]);
+                if (p.tpe_bm_rows) {
+                    // lattices of at most 32 padded columns: ONE word per row, so an agent at (cx, cy) reads the three
+                    // rows around it once and tests four bits (cell = cy * PW + cx)
+                    for (int w = 0; w < p.tpe_bm_words; ++w) bm_store((unsigned)w, ~walk_row[w]);
 #pragma unroll
-                for (int k = 0; k < A; ++k)
-                    if (fl[k] & CC_F_ACTIVE) bm_store((unsigned)cell[k] >> 5, bm_load((unsigned)cell[k] >> 5) | (1u << (cell[k] & 31)));
+                    for (int k = 0; k < A; ++k)
+                        if (fl[k] & CC_F_ACTIVE) {
+                            const unsigned cy = min(pos[k] & 0xffu, (unsigned)p.H) + 1u, cx = min(pos[k] >> 8, (unsigned)p.W) + 1u;
+                            bm_store(cy, bm_load(cy) | (1u << cx));
+                        }
 #pragma unroll
-                for (int k = 0; k < A; ++k) {
-                    const int c = cell[k];
-                    auto blocked = [&](int idx) { return (bm_load((unsigned)idx >> 5) >> (idx & 31)) & 1u; };
-                    vmask[k] = (blocked(c + 1) | (blocked(c + PW) << 1) | (blocked(c - 1) << 2) | (blocked(c - PW) << 3)) ^ 15u;
+                    for (int k = 0; k < A; ++k) {
+                        const unsigned cy = min(pos[k] & 0xffu, (unsigned)p.H) + 1u, cx = min(pos[k] >> 8, (unsigned)p.W) + 1u;
+                        const unsigned below = bm_load(cy - 1u), here = bm_load(cy), above = bm_load(cy + 1u);
+                        const unsigned blocked = ((here >> (cx + 1u)) & 1u) | (((above >> cx) & 1u) << 1) | (((here >> (cx - 1u)) & 1u) << 2) | (((below >> cx) & 1u) << 3);
+                        vmask[k] = blocked ^ 15u;
+                    }
+                } else {
+                    for (int w = 0; w < p.tpe_bm_words; ++w) bm_store((unsigned)w, ~walk[w]);
+#pragma unroll
+                    for (int k = 0; k < A; ++k)
+                        if (fl[k] & CC_F_ACTIVE) bm_store((unsigned)cell[k] >> 5, bm_load((unsigned)cell[k] >> 5) | (1u << (cell[k] & 31)));
+#pragma unroll
+                    for (int k = 0; k < A; ++k) {
+                        const int c = cell[k];
+                        auto blocked = [&](int idx) { return (bm_load((unsigned)idx >> 5) >> (idx & 31)) & 1u; };
+                        vmask[k] = (blocked(c + 1) | (blocked(c + PW) << 1) | (blocked(c - 1) << 2) | (blocked(c - PW) << 3)) ^ 15u;
+                    }
                 }
             } else {
 #pragma unroll

@@ -66,6 +66,7 @@ struct KParams {
     long long n_groups;
     int smem_total;
     int tpe_bm_words;    // thread-per-env kernel: words of the private lattice bitmap (0 = compare-based occupancy)
+    int tpe_bm_rows;     // ... 1: one word per padded lattice ROW (at most 32 padded columns), else bit index = cell
     unsigned *tpe_counter, *tpe_counter_next;   // thread-per-env kernel: work counters of this / the next launch
     int tpe_reverse;              // step kernels: process the groups from the last to the first (alternates between launches)
     // thread-per-env kernel, fused multi-step launches (cc_rollout_fused): every output is time-major [n_steps][...]
