@@ -15,6 +15,9 @@
 
 #include "../../include/ccb200.h"
 
+#ifndef CCB_MIN_BLOCKS_APL2
+#define CCB_MIN_BLOCKS_APL2 1   // crews of 33-64 agents (two agents per lane): 108 registers, 2 CTAs per SM (3 CTAs at 76 registers measured slower: 1.63 vs 1.49 ms int8, 3.04 vs 2.77 ms float32 per 262 k envs)
+#endif
 #ifndef CCB_MIN_BLOCKS
 #define CCB_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must allow (A/B in DESIGN.md §6)
 #endif
@@ -289,7 +292,7 @@ __device__ __forceinline__ int greedy_decision(int row, unsigned vmask) {
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
 template <int LPE, int APL, int OBS, int MODE>
-__global__ void __launch_bounds__(kThreads, (APL == 1 && MODE == kModeStep) ? CCB_MIN_BLOCKS : 1) cc_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 ? CCB_MIN_BLOCKS : (APL == 2 ? CCB_MIN_BLOCKS_APL2 : 1))) cc_kernel(const __grid_constant__ KParams p) {
     using TL_ = Tile<LPE, APL>;
     using OT = typename std::conditional<OBS == CC_OBS_FP32, float, int8_t>::type;
     using P2 = typename PairOf<OT>::type;
