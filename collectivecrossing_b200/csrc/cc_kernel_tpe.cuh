@@ -78,9 +78,9 @@ struct TpeLayout {
     // 32-unit rows, so unit j of lane l lies at the same place of every block and ONE table entry per
     // (j, lane) — the offset of its source from the block's first template — serves all blocks.
     //   float32: unit = one 8-byte pair (lane <-> pair).  A warp instruction gathers 32 CONSECUTIVE output
-    //            pairs; but for the own position these are consecutive template pairs or constants, so
-    //            the gather is free of bank conflicts inside an env, and it stores 256 contiguous bytes
-    //            (measured against 16-byte vectors assembled from two gathers: 2-way conflicts on every load).
+    //            pairs: but for the own position, the door constants and the masked block these are
+    //            consecutive template pairs (2-way bank conflicts at most, none with CCB_TPE_CONST_REGS).
+    //            With TMA rows the table has one entry per (j, lane) for ANY env (offset inside its template).
     //   int8:    unit = one 16-byte vector of 8 pairs.
     static constexpr bool kPairwise = OBS == CC_OBS_FP32;
     static constexpr int UPE = kPairwise ? PPE : VPE;    // emission units per env
