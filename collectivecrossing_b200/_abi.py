@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_AGENTS = 128
 
 # cc_status
@@ -13,7 +13,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_INVALID_ACTION, ERR_RESET_ST
 
 REWARD_KINDS = {"default": 0, "simple_distance": 1, "binary": 2, "constant_negative": 3}
 TERMINATED_KINDS = {"individual_at_destination": 0, "all_at_destination": 1}
-OBS_NONE, OBS_INT8, OBS_FP32 = 0, 1, 4
+OBS_NONE, OBS_INT8, OBS_FP32, OBS_TABLE = 0, 1, 4, 16
 REWARD_F32, REWARD_F64 = 4, 8
 POLICIES = {"external": 0, "random": 1, "greedy": 2, "waiting": 3}
 
@@ -75,6 +75,14 @@ EXPORTS = {
     "cc_get_state_host": (C.c_int, [_P, _P, _P, _P, _P]),
     "cc_step": (C.c_int, [_P, C.POINTER(CCStepIO), _P]),
     "cc_step_host": (C.c_int, [_P, C.POINTER(CCStepIO)]),
+    "cc_rollout_host": (C.c_int, [_P, C.POINTER(CCStepIO), _I32]),
+    "cc_set_host_chunk": (C.c_int, [_P, _I64]),
+    "cc_set_host_expand": (C.c_int, [_P, _I32]),
+    "cc_order_after": (C.c_int, [_P, _P]),
+    "cc_expand_obs_host": (C.c_int, [C.POINTER(CCConfig), _I64, _P, _P, _I32, _I32]),
+    "cc_get_rng_state": (C.c_int, [_P, _P, _P]),
+    "cc_set_rng_state": (C.c_int, [_P, _P, _P]),
+    "cc_rng_seeded": (_I32, [_P]),
     "cc_rollout": (C.c_int, [_P, C.POINTER(CCStepIO), _I32, _P]),
     "cc_rollout_fused": (C.c_int, [_P, C.POINTER(CCStepIO), _I32, _P]),
     "cc_reset": (C.c_int, [_P, _P, _P, _I32, _P]),

@@ -25,7 +25,8 @@ import torch
 from . import _abi, _native
 from .lowering import lower_config
 
-_OBS_TORCH = {"none": (None, _abi.OBS_NONE), "int8": (torch.int8, _abi.OBS_INT8), "float32": (torch.float32, _abi.OBS_FP32)}
+_OBS_TORCH = {"none": (None, _abi.OBS_NONE), "int8": (torch.int8, _abi.OBS_INT8), "float32": (torch.float32, _abi.OBS_FP32),
+              "table": (torch.int8, _abi.OBS_TABLE)}
 _REW_TORCH = {"float32": (torch.float32, _abi.REWARD_F32), "float64": (torch.float64, _abi.REWARD_F64)}
 
 
@@ -33,7 +34,7 @@ _REW_TORCH = {"float32": (torch.float32, _abi.REWARD_F32), "float64": (torch.flo
 class StepOutput:
     """Views of the env's output tensors after a step (valid until the next step)."""
 
-    obs: torch.Tensor | None      # [N, A, 6+4A]
+    obs: torch.Tensor | None      # [N, A, 6+4A]; [N, A, 4] int8 (x, y, type, active) with obs_dtype="table"
     reward: torch.Tensor          # [N, A]; 0 where the agent had no reward entry
     agent_flags: torch.Tensor     # [N, A] CC_O_* bits
     agent_info: torch.Tensor | None  # [N, A] CC_I_* bits
@@ -117,7 +118,9 @@ class BatchedCollectiveCrossing:
         self.flags = torch.zeros((n, a), dtype=torch.uint8, device=dev)
         self.step_count = torch.zeros((n,), dtype=torch.int32, device=dev)
         self.episode_return = torch.zeros((n,), dtype=torch.float32, device=dev)
-        self.obs = None if self.obs_code == _abi.OBS_NONE else torch.zeros((n, a, self.obs_len), dtype=self.obs_torch_dtype, device=dev)
+        # last axis of the obs output: the reference's row (6+4A) or one block of the compact table
+        self.obs_width = 4 if self.obs_code == _abi.OBS_TABLE else self.obs_len
+        self.obs = None if self.obs_code == _abi.OBS_NONE else torch.zeros((n, a, self.obs_width), dtype=self.obs_torch_dtype, device=dev)
         self.reward = torch.zeros((n, a), dtype=self.reward_torch_dtype, device=dev)
         self.agent_flags = torch.zeros((n, a), dtype=torch.uint8, device=dev)
         self.agent_info = torch.zeros((n, a), dtype=torch.uint8, device=dev) if with_info else None
@@ -175,13 +178,25 @@ class BatchedCollectiveCrossing:
         self.episode_return.zero_()
 
     def get_state(self) -> dict:
-        return {"x": self.x.clone(), "y": self.y.clone(), "flags": self.flags.clone(), "step_count": self.step_count.clone(),
-                "episode_return": self.episode_return.clone(), "t": int(self._lib.cc_step_counter(self._h))}
+        """Checkpoint: env state, the Philox counter and — once ``reset_seeded`` has seeded them — the per-env
+        numpy-compatible generators (what gymnasium keeps in ``env.np_random``), so that a resumed run's
+        unseeded ``reset()`` continues the saved run's stream."""
+        state = {"x": self.x.clone(), "y": self.y.clone(), "flags": self.flags.clone(), "step_count": self.step_count.clone(),
+                 "episode_return": self.episode_return.clone(), "t": int(self._lib.cc_step_counter(self._h)), "rng": None}
+        if int(self._lib.cc_rng_seeded(self._h)):
+            rng = torch.zeros((self.num_envs, 6), dtype=torch.int64, device=self.device)   # uint64 bit patterns
+            _native.check(self._lib.cc_get_rng_state(self._h, rng.data_ptr(), self._stream()))
+            state["rng"] = rng
+        return state
 
     def load_state(self, state: dict) -> None:
         self.set_state(state["x"], state["y"], state["flags"], state["step_count"])
         self.episode_return.copy_(state["episode_return"])
         _native.check(self._lib.cc_set_step_counter(self._h, int(state["t"])))
+        if state.get("rng") is not None:
+            rng = self._check_tensor(state["rng"].to(self.device), torch.int64, (self.num_envs, 6), "rng")
+            _native.check(self._lib.cc_set_rng_state(self._h, rng.data_ptr(), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()   # `rng` may be a temporary
 
     # ---- reset ---------------------------------------------------------------------------------
     def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor | None:
@@ -265,7 +280,7 @@ class BatchedCollectiveCrossing:
         if buf is None or buf["reward"].shape[0] != T:
             dev = self.device
             buf = self._traj = dict(
-                obs=None if self.obs is None else torch.zeros((T, n, a, self.obs_len), dtype=self.obs_torch_dtype, device=dev),
+                obs=None if self.obs is None else torch.zeros((T, n, a, self.obs_width), dtype=self.obs_torch_dtype, device=dev),
                 reward=torch.zeros((T, n, a), dtype=self.reward_torch_dtype, device=dev),
                 agent_flags=torch.zeros((T, n, a), dtype=torch.uint8, device=dev),
                 agent_info=None if self.agent_info is None else torch.zeros((T, n, a), dtype=torch.uint8, device=dev),
@@ -302,36 +317,94 @@ class BatchedCollectiveCrossing:
         return self.obs
 
     # ---- host-buffer path (what a numpy / RLlib caller binds) --------------------------------------
-    def make_host_buffers(self, pinned: bool = True) -> dict:
+    def make_host_buffers(self, pinned: bool = True, n_steps: int | None = None, obs: str | None = "same") -> dict:
+        """Host tensors for ``step_host`` (``n_steps=None``: per-step shapes) or ``rollout_host``
+        (time-major ``[n_steps, ...]``).  ``obs``: "same" = the env's obs dtype, or "float32" / "int8" /
+        "table" / None for another delivery format of the same step."""
         n, a = self.num_envs, self.num_agents
-        mk = lambda shape, dt: torch.zeros(shape, dtype=dt, pin_memory=pinned)  # noqa: E731
+        lead = () if n_steps is None else (int(n_steps),)
+        mk = lambda shape, dt: torch.zeros(lead + shape, dtype=dt, pin_memory=pinned)  # noqa: E731
+        if obs == "same":
+            obs_t = None if self.obs is None else mk((n, a, self.obs_width), self.obs_torch_dtype)
+        elif obs is None or obs == "none":
+            obs_t = None
+        else:
+            dt, code = _OBS_TORCH[obs]
+            obs_t = mk((n, a, 4 if code == _abi.OBS_TABLE else self.obs_len), dt)
         return dict(
-            actions=mk((n, a), torch.int8),
-            obs=None if self.obs is None else mk((n, a, self.obs_len), self.obs_torch_dtype),
+            actions=mk((n, a), torch.int8), obs=obs_t,
             reward=mk((n, a), self.reward_torch_dtype), agent_flags=mk((n, a), torch.uint8),
             agent_info=None if self.agent_info is None else mk((n, a), torch.uint8),
             env_flags=mk((n,), torch.uint8), actions_out=mk((n, a), torch.int8),
         )
 
-    def step_host(self, host: dict, *, policy: Any = "external", auto_reset: bool | None = None) -> dict:
-        """``cc_step_host``: actions are read from HOST memory (``host['actions']``), the outputs
-        land in the HOST tensors of ``host``; the call returns when they are complete."""
+    def _host_io(self, host: dict, policy: Any, auto_reset: bool | None) -> _abi.CCStepIO:
         io = _abi.CCStepIO()
         code = _policy_code(policy)
         io.actions = host["actions"].data_ptr() if code == 0 else None
         io.order = None
         io.actions_out = host["actions_out"].data_ptr()
-        io.obs = None if host["obs"] is None else host["obs"].data_ptr()
+        obs = host["obs"]
+        io.obs = None if obs is None else obs.data_ptr()
         io.reward = host["reward"].data_ptr()
         io.agent_flags = host["agent_flags"].data_ptr()
         io.agent_info = None if host.get("agent_info") is None else host["agent_info"].data_ptr()
         io.env_flags = host["env_flags"].data_ptr()
-        io.obs_dtype = self.obs_code if host["obs"] is not None else _abi.OBS_NONE
+        if obs is None:
+            io.obs_dtype = _abi.OBS_NONE
+        elif obs.dtype == torch.float32:
+            io.obs_dtype = _abi.OBS_FP32
+        else:
+            io.obs_dtype = _abi.OBS_TABLE if obs.shape[-1] == 4 else _abi.OBS_INT8
         io.reward_dtype = self.reward_code
         io.policy = code
         io.auto_reset = int(self.auto_reset if auto_reset is None else auto_reset)
+        # everything enqueued on the current torch stream so far (set_state copies, earlier steps) happens first
+        _native.check(self._lib.cc_order_after(self._h, self._stream()))
+        return io
+
+    def step_host(self, host: dict, *, policy: Any = "external", auto_reset: bool | None = None) -> dict:
+        """``cc_step_host``: actions are read from HOST memory (``host['actions']``), the outputs
+        land in the HOST tensors of ``host``; the call returns when they are complete.  Chunks of envs
+        are pipelined over three streams (copy in / kernel / copy out)."""
+        io = self._host_io(host, policy, auto_reset)
         _native.check(self._lib.cc_step_host(self._h, C.byref(io)))
         return host
+
+    def rollout_host(self, host: dict, n_steps: int, *, policy: Any = "greedy", auto_reset: bool | None = None) -> dict:
+        """``cc_rollout_host``: ``n_steps`` env-steps per env, every output time-major in the HOST tensors of
+        ``host`` (``make_host_buffers(n_steps=T)``); chunks of envs are rolled out on the device while the
+        previous chunk's slices stream to the host."""
+        if host["reward"].shape[0] != int(n_steps):
+            raise ValueError("host buffers must be time-major with n_steps slices: make_host_buffers(n_steps=T)")
+        io = self._host_io(host, policy, auto_reset)
+        _native.check(self._lib.cc_rollout_host(self._h, C.byref(io), int(n_steps)))
+        return host
+
+    def set_host_chunk(self, chunk_envs: int) -> None:
+        """Envs per chunk of the host pipeline (0 = automatic)."""
+        _native.check(self._lib.cc_set_host_chunk(self._h, int(chunk_envs)))
+
+    def set_host_expand(self, n_threads: int) -> None:
+        """Rows of the host path rebuilt on the host from the compact table (``n_threads`` host threads, -1 = all,
+        0 = off: rows cross PCIe as the kernel wrote them).  Same bytes either way."""
+        _native.check(self._lib.cc_set_host_expand(self._h, int(n_threads)))
+
+    def expand_table_host(self, table: torch.Tensor, out: torch.Tensor | None = None, dtype: torch.dtype = torch.float32,
+                          n_threads: int = 0) -> torch.Tensor:
+        """``cc_expand_obs_host``: HOST table ``[..., A, 4]`` int8 -> the reference's rows ``[..., A, 6+4A]``
+        (observations.py:62-94), bit-identical to the kernels' ``float32`` / ``int8`` rows."""
+        if table.device.type != "cpu" or table.dtype != torch.int8 or not table.is_contiguous() or tuple(table.shape[-2:]) != (self.num_agents, 4):
+            raise ValueError(f"table must be a contiguous int8 CPU tensor of shape [..., {self.num_agents}, 4]")
+        shape = tuple(table.shape[:-1]) + (self.obs_len,)
+        if out is None:
+            out = torch.empty(shape, dtype=dtype)
+        if out.device.type != "cpu" or tuple(out.shape) != shape or not out.is_contiguous() or out.dtype not in (torch.float32, torch.int8):
+            raise ValueError(f"out must be a contiguous float32 / int8 CPU tensor of shape {shape}")
+        code = _abi.OBS_FP32 if out.dtype == torch.float32 else _abi.OBS_INT8
+        n = table.numel() // (4 * self.num_agents)
+        _native.check(self._lib.cc_expand_obs_host(C.byref(self.cfg), n, table.data_ptr(), out.data_ptr(), code, int(n_threads)))
+        return out
 
     # ---- bookkeeping -----------------------------------------------------------------------------
     def stats(self) -> dict:
@@ -367,4 +440,6 @@ class BatchedCollectiveCrossing:
     # algorithmic bytes of one env-step (SURVEY.md §8d / DESIGN.md §5)
     def algorithmic_bytes_per_env_step(self) -> int:
         a = self.num_agents
+        if self.obs_code == _abi.OBS_TABLE:   # s_obs = 0 plus the 4A-byte table
+            return 12 * a + 17 + 4 * a
         return 12 * a + 17 + self.obs_code * a * (6 + 4 * a)

@@ -49,7 +49,7 @@ template <int A, int OBS>
 struct TpeLayout {
     using OT = typename std::conditional<OBS == CC_OBS_FP32, float, int8_t>::type;
     using P2 = typename PairOf<OT>::type;
-    static constexpr bool kHasObs = OBS != CC_OBS_NONE;
+    static constexpr bool kHasObs = OBS == CC_OBS_INT8 || OBS == CC_OBS_FP32;   // the reference's rows (CC_OBS_TABLE needs no staging)
     static constexpr int R = 3 + 2 * A;                  // pairs per observation row
     static constexpr int PPE = A * R;                    // pairs per env
     static constexpr int PSZ = (int)sizeof(P2);          // 8 (float32) or 2 (int8)
@@ -672,6 +672,24 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         if (env_ok) __stcs(reinterpret_cast<unsigned char *>(p.env_flags) + (size_t)tt * (size_t)p.slice_envs + n, (unsigned char)eflags);
 #pragma unroll
         for (int k = 0; k < A; ++k) fl[k] &= 7u;
+
+        // ---- CC_OBS_TABLE: (x_j, y_j, type_j, active_j) of observations.py:80-91 from the post-step (post-reset) state,
+        // one 32-bit word per agent: an env's 4A bytes leave the thread as 16-byte vectors (A = 4, 8) or words ----
+        if constexpr (OBS == CC_OBS_TABLE) {
+            if (env_ok) {
+                unsigned tw[A];
+#pragma unroll
+                for (int k = 0; k < A; ++k) tw[k] = (pos[k] >> 8) | ((pos[k] & 0xffu) << 8) | ((k < p.B ? 0u : 1u) << 16) | ((fl[k] & 1u) << 24);
+                unsigned *dst = reinterpret_cast<unsigned *>(static_cast<unsigned char *>(p.obs) + (size_t)tt * (size_t)p.slice_obs_bytes) + (size_t)n * A;
+                if constexpr (A % 4 == 0) {
+#pragma unroll
+                    for (int k = 0; k < A; k += 4) __stcs(reinterpret_cast<uint4 *>(dst + k), make_uint4(tw[k], tw[k + 1], tw[k + 2], tw[k + 3]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < A; ++k) __stcs(dst + k, tw[k]);
+                }
+            }
+        }
 
         // ---- observations.py:43-94 from the post-step (post-reset) state --------------------------
         if (kHasObs) {

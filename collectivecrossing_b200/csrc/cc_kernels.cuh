@@ -298,7 +298,8 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
     using P2 = typename PairOf<OT>::type;
     constexpr int EPW = TL_::EPW;
     constexpr int PPV = 16 / (int)sizeof(P2);  // output pairs per 16-byte vector: 2 (fp32) or 8 (int8)
-    constexpr bool kHasObs = OBS != CC_OBS_NONE;
+    constexpr bool kHasObs = OBS == CC_OBS_INT8 || OBS == CC_OBS_FP32;   // the reference's rows
+    constexpr bool kTable = OBS == CC_OBS_TABLE;                            // the compact [A][4] table
     constexpr bool kCanCache = kHasObs && LPE <= 16;
     constexpr bool kHasPolicy = MODE == kModeStep || MODE == kModePolicy;
     constexpr bool kMoves = MODE == kModeStep;
@@ -832,6 +833,16 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
             }
         }
 
+        // ---- CC_OBS_TABLE: (x_j, y_j, type_j, active_j) of observations.py:80-91, one 32-bit word per agent ----
+        if (kTable && p.obs != nullptr) {
+            const bool wr = env_ok && (MODE != kModeReset || need_reset);   // reset: only the envs that were reset
+            unsigned *tab = reinterpret_cast<unsigned *>(p.obs) + p.obs_env_offset * A;
+#pragma unroll
+            for (int k = 0; k < APL; ++k)
+                if (wr && avalid[k])
+                    __stcs(tab + off[k], (pos[k] >> 8 & 0xffu) | ((pos[k] & 0xffu) << 8) | ((aidx[k] < p.B ? 0u : 1u) << 16) | ((fl[k] & 1u) << 24));
+        }
+
         // ---- observations.py:43-94 from the post-step (post-reset) state ------------------------
         if (kHasObs && p.obs != nullptr) {
             P2 *tstage = stage + T.tile * (2 * A + 4) + 3;
@@ -1021,6 +1032,8 @@ struct Pcg64State { unsigned long long hi, lo, inc_hi, inc_lo, buffered, has_buf
 
 // seeds != nullptr: reset(seed=seeds[n]) — a fresh generator per env (gymnasium Env.reset(seed=s));
 // seeds == nullptr: reset() — every env keeps drawing from its stored generator.
+// (a plain function, not a template: defined in the one translation unit that sets CCB_WITH_RESET_SEEDED)
+#ifdef CCB_WITH_RESET_SEEDED
 __global__ void __launch_bounds__(128) cc_reset_seeded_kernel(const __grid_constant__ KParams p, const long long *seeds, Pcg64State *gen) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.n_envs) return;
@@ -1055,5 +1068,6 @@ __global__ void __launch_bounds__(128) cc_reset_seeded_kernel(const __grid_const
     gen[n] = Pcg64State{g.hi, g.lo, g.inc_hi, g.inc_lo, (unsigned long long)g.buffered, g.has_buffered ? 1ull : 0ull};
     if (stuck) atomicOr(p.err, kErrResetStuck);
 }
+#endif  // CCB_WITH_RESET_SEEDED
 
 }  // namespace ccb

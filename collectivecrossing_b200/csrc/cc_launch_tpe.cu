@@ -1,0 +1,71 @@
+// cc_launch_tpe.cu — instantiations and launcher of ccb::cc_step_tpe_kernel (one thread per env, cc_kernel_tpe.cuh).
+// Host-side plumbing only.  CCB_TPE_PART (0 / 1) splits the crews over two objects so that they compile in parallel.
+#include "cc_internal.h"
+#include "cc_kernel_tpe.cuh"
+
+#ifndef CCB_TPE_PART
+#error "compile with -DCCB_TPE_PART=0 (crews 1-4 and 8-agent int8 rows) or 1 (crews 5-8)"
+#endif
+
+namespace {
+
+using ccb::KParams;
+
+template <int A, int OBS>
+int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
+    using L = ccb::TpeLayout<A, OBS>;
+    auto kern = ccb::cc_step_tpe_kernel<A, OBS>;
+    p.n_groups = (p.n_envs + 31) / 32;
+    // greedy / waiting: a private lattice bitmap per thread while the lattice is small (README: 6 words)
+    const bool on_device_policy = p.policy == CC_POLICY_GREEDY || p.policy == CC_POLICY_WAITING;
+    // (with TMA rows the bitmap aliases the warp's image ring: 128 bytes per word)
+    const int bm_cap = L::kTma ? (L::kImgRing * L::kImgBytes / 128 < ccb::kTpeMaxBitmapWords ? L::kImgRing * L::kImgBytes / 128 : ccb::kTpeMaxBitmapWords)
+                               : ccb::kTpeMaxBitmapWords;
+    p.tpe_bm_words = (on_device_policy && p.walk_words <= bm_cap) ? p.walk_words : 0;
+    // one word per lattice row where the padded lattice has at most 32 columns and its rows fit the bitmap (README: 11 rows)
+    if (on_device_policy && p.W + 3 <= 32 && p.H + 3 <= bm_cap) { p.tpe_bm_words = p.H + 3; p.tpe_bm_rows = 1; }
+    // launch k counts its groups in counter k & 1 and zeroes the other one for launch k + 1 (launches of
+    // one handle are stream-ordered by contract)
+    if (p.n_steps < 1) p.n_steps = 1;
+    p.tpe_counter = h->tpe_counters + (h->tpe_launches & 1);
+    p.tpe_counter_next = h->tpe_counters + ((h->tpe_launches + 1) & 1);
+    // (with TMA rows the bitmap aliases the warp's image ring)
+    const int smem = L::kStageBytes + (L::kTma ? 0 : p.tpe_bm_words * ccb::kTpeThreads * 4);
+    int per_sm = 0;
+    int rc = cc_cached_occupancy(h, reinterpret_cast<const void *>(kern), ccb::kTpeThreads, smem, &per_sm);
+    if (rc != CC_OK) return rc;
+    long long want = (p.n_groups + ccb::kTpeWarps - 1) / ccb::kTpeWarps;
+    long long cap = (long long)h->sm_count * per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, ccb::kTpeThreads, smem, s>>>(p);
+    CC_CUDA(cudaGetLastError());
+    h->launches += 1;
+    h->tpe_launches += 1;
+    return CC_OK;
+}
+
+}  // namespace
+
+#define CCB_TPE_CASES(A_)                                                                   \
+    case A_ * 32 + CC_OBS_NONE: return launch_tpe_t<A_, CC_OBS_NONE>(h, p, s);                  \
+    case A_ * 32 + CC_OBS_TABLE: return launch_tpe_t<A_, CC_OBS_TABLE>(h, p, s);                \
+    case A_ * 32 + CC_OBS_FP32: return launch_tpe_t<A_, CC_OBS_FP32>(h, p, s);
+
+#if CCB_TPE_PART == 0
+int cc_launch_tpe_part0(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s) {
+    switch (p.A * 32 + obs_dtype) {
+        CCB_TPE_CASES(1) CCB_TPE_CASES(2) CCB_TPE_CASES(3) CCB_TPE_CASES(4)
+    case 8 * 32 + CC_OBS_INT8: return launch_tpe_t<8, CC_OBS_INT8>(h, p, s);
+    }
+    return cc_fail(CC_ERR_UNSUPPORTED, "no thread-per-env kernel for %d agents, obs_dtype %d", p.A, obs_dtype);
+}
+#else
+int cc_launch_tpe_part0(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s);
+int cc_launch_tpe(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s) {
+    switch (p.A * 32 + obs_dtype) {
+        CCB_TPE_CASES(5) CCB_TPE_CASES(6) CCB_TPE_CASES(7) CCB_TPE_CASES(8)
+    }
+    return cc_launch_tpe_part0(h, p, obs_dtype, s);
+}
+#endif

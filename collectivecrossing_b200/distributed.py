@@ -79,6 +79,14 @@ class ShardedCollectiveCrossing:
             from .batched import BatchedCollectiveCrossing
 
             if device is None:
+                # one process per GPU under torchrun: the rank's own device, not whatever happens to be current
+                import os
+
+                local = os.environ.get("LOCAL_RANK")
+                if local is not None:
+                    torch.cuda.set_device(int(local))
+                elif self.world_size > 1:
+                    raise ValueError("world_size > 1 without LOCAL_RANK: pass device=... (every rank would land on cuda:0)")
                 device = torch.device("cuda", torch.cuda.current_device())
             env_factory = lambda cfg, n, **kw: BatchedCollectiveCrossing(cfg, n, device, **kw)  # noqa: E731
         self.device = device

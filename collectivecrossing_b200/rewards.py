@@ -11,7 +11,7 @@ from __future__ import annotations
 
 from typing import Any
 
-from ._strategies import evaluate, registry_get
+from ._strategies import evaluate, is_done, registry_get
 
 
 class RewardFunction:
@@ -21,6 +21,8 @@ class RewardFunction:
         self.reward_config = reward_config
 
     def calculate_reward(self, agent_id: str, env: Any) -> float | None:
+        if is_done(agent_id, env):   # rewards.py:65-66: no arithmetic, answered without a launch (any env object)
+            return None
         return evaluate(env, reward_config=self.reward_config)["rewards"].get(agent_id)
 
 

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 from typing import Any
 
-from ._strategies import evaluate, registry_get
+from ._strategies import evaluate, is_done, registry_get
 
 
 class TruncatedFunction:
@@ -16,6 +16,8 @@ class TruncatedFunction:
         self.truncated_config = truncated_config
 
     def calculate_truncated(self, agent_id: str, env: Any) -> bool | None:
+        if is_done(agent_id, env):   # truncateds.py:57-58
+            return None
         return evaluate(env, truncated_config=self.truncated_config)["truncateds"].get(agent_id)
 
 

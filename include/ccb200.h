@@ -16,6 +16,15 @@
  * Buffers: unless stated otherwise every pointer is a DEVICE pointer on the
  * handle's device, borrowed for the duration of the call.  The *_host entry
  * points take HOST pointers (pinned or pageable) and perform the copies.
+ *
+ * Stream order: every call that takes a `stream` enqueues its work there and
+ * returns without waiting; calls on one handle must be issued in the order
+ * they are meant to run.  The handle records an event behind each of them, and
+ * the *_host entry points (which use the handle's own copy / compute streams)
+ * wait for that event first and return only when their outputs are complete —
+ * so step() / reset() on a caller stream followed by step_host() needs no
+ * synchronisation by the caller.  A caller that switches from one stream to
+ * another between two calls orders the two streams itself.
  */
 #ifndef CCB200_H
 #define CCB200_H
@@ -26,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CCB200_ABI_VERSION 1
+#define CCB200_ABI_VERSION 2
 #define CC_MAX_AGENTS 128 /* num_boarding + num_exiting supported by the kernels */
 
 typedef enum cc_status {
@@ -54,11 +63,16 @@ typedef enum cc_terminated_kind {
     CC_TERM_ALL_AT_DESTINATION = 1         /* terminateds.py:37-60 */
 } cc_terminated_kind;
 
-/* element size of the materialised observation tensor (s_obs in SURVEY.md §8d) */
+/* what `obs` receives.  INT8 / FP32: the reference's observation tensor [N,A,6+4A] (the value is the
+ * element size, s_obs in SURVEY.md §8d).  TABLE: the compact form of the same information (s_obs = 0
+ * of SURVEY.md §8d): per env the int8 table [A][4] = (x_j, y_j, type_j, active_j) of
+ * observations.py:80-91; every row of observations.py:62-94 is this table with block i replaced by
+ * -1, preceded by (x_i, y_i) and four per-config constants — cc_expand_obs_host rebuilds the rows. */
 typedef enum cc_obs_dtype {
-    CC_OBS_NONE = 0, /* observations not materialised (compact state only) */
+    CC_OBS_NONE = 0, /* observations not materialised */
     CC_OBS_INT8 = 1,
-    CC_OBS_FP32 = 4  /* the reference's dtype (observations.py:94) */
+    CC_OBS_FP32 = 4, /* the reference's dtype (observations.py:94) */
+    CC_OBS_TABLE = 16 /* int8 [N,A,4] */
 } cc_obs_dtype;
 
 typedef enum cc_reward_dtype {
@@ -128,7 +142,7 @@ typedef struct cc_step_io {
                               * (the caller's action_dict order, collectivecrossing.py:197);    *
                               * a negative entry ends the list; NULL = agent order 0..A-1       */
     int8_t *actions_out;     /* [N,A] nullable: the actions that were applied                  */
-    void *obs;               /* [N,A,6+4A] of obs_dtype, nullable iff obs_dtype == CC_OBS_NONE */
+    void *obs;               /* [N,A,6+4A] of obs_dtype ([N,A,4] int8 for CC_OBS_TABLE), nullable iff CC_OBS_NONE */
     void *reward;            /* [N,A] of reward_dtype (0 where !CC_O_ALIVE_PREV)               */
     uint8_t *agent_flags;    /* [N,A] CC_O_* bits                                               */
     uint8_t *agent_info;     /* [N,A] CC_I_* bits, nullable                                     */
@@ -186,10 +200,39 @@ int cc_get_state_host(cc_handle *h, int8_t *x, int8_t *y, uint8_t *flags, int32_
  * handle in ONE fused kernel launch on `stream` (a cudaStream_t; NULL = legacy default). */
 int cc_step(cc_handle *h, const cc_step_io *io, void *stream);
 
-/* Same with every pointer of `io` a HOST pointer: copies actions (and order) host->device,
- * launches the kernel, copies the outputs device->host and waits.  This is the call a
- * non-CUDA caller (numpy, the reference's RLlib env-runner) binds. */
+/* Same with every pointer of `io` a HOST pointer (pinned for full PCIe speed, pageable works).
+ * This is the call a non-CUDA caller (numpy, the reference's RLlib env-runner) binds.  The envs
+ * are processed in chunks on three streams of the handle — chunk c+1's host->device copy of
+ * the actions and its kernel overlap chunk c's device->host copies of the outputs — and the call
+ * returns when every output is complete in host memory. */
 int cc_step_host(cc_handle *h, const cc_step_io *io);
+
+/* cc_rollout_fused with HOST pointers: n_steps env-steps per env, every output time-major
+ * [n_steps][N]... in host memory (io->actions [n_steps][N][A] when the policy is EXTERNAL).  Chunks of
+ * envs are rolled out one after the other (one fused launch per chunk where the thread-per-env
+ * kernel applies) while the previous chunk's slices stream to the host. */
+int cc_rollout_host(cc_handle *h, const cc_step_io *io, int32_t n_steps);
+
+/* Envs per chunk of the host pipeline (0 = automatic: about N/8, a multiple of 32). */
+int cc_set_host_chunk(cc_handle *h, int64_t chunk_envs);
+
+/* Row delivery of the host path.  n_threads == 0 (default): CC_OBS_INT8 / CC_OBS_FP32 rows are written by the
+ * kernel and cross PCIe as they are.  n_threads != 0: the kernel writes the compact table, the table crosses
+ * PCIe (4A bytes per env instead of s_obs*A*(6+4A)) and cc_expand_obs_host rebuilds the rows in the caller's
+ * buffer on n_threads host threads (< 0: all hardware threads), chunk by chunk while later chunks are still
+ * on the device.  The bytes that arrive are identical either way. */
+int cc_set_host_expand(cc_handle *h, int32_t n_threads);
+
+/* Make the next *_host call wait for everything enqueued on `stream` so far (for work the library cannot see:
+ * a caller that owns the state tensors — cc_attach_state — and writes them with its own kernels or copies). */
+int cc_order_after(cc_handle *h, void *stream);
+
+/* Host-side expansion of CC_OBS_TABLE output into the reference's observation rows
+ * (observations.py:62-94): table int8 [n_envs][A][4] -> obs [n_envs][A][6+4A] of obs_dtype
+ * (CC_OBS_INT8 or CC_OBS_FP32), bit-identical to what the kernels write for that dtype.  Pure
+ * data movement on `n_threads` host threads (0 = all hardware threads); no CUDA call. */
+int cc_expand_obs_host(const cc_config *cfg, int64_t n_envs, const int8_t *table, void *obs,
+                       int32_t obs_dtype, int32_t n_threads);
 
 /* T fused steps with an on-device policy and auto-reset (one launch per step, no host
  * round-trip, outputs of the last step only). */
@@ -217,6 +260,15 @@ int cc_reset(cc_handle *h, const uint8_t *mask, void *obs, int32_t obs_dtype, vo
  * last seeded with (gymnasium keeps env.np_random across resets); an error before any seeding. */
 int cc_reset_seeded(cc_handle *h, const int64_t *seeds, void *obs, int32_t obs_dtype,
                     void *stream);
+
+/* Checkpoint of the per-env numpy-compatible generators cc_reset_seeded keeps (what gymnasium holds
+ * in env.np_random): uint64 [N][6] = {state hi, state lo, inc hi, inc lo, buffered uint32,
+ * has_buffered}.  cc_get_rng_state fails before the first seeded reset; cc_set_rng_state marks the
+ * generators as seeded, so a resumed run's reset() continues the stream of the saved run. */
+int cc_get_rng_state(cc_handle *h, uint64_t *out, void *stream);
+int cc_set_rng_state(cc_handle *h, const uint64_t *in, void *stream);
+/* 1 once the generators hold a stream (after cc_reset_seeded(seeds) or cc_set_rng_state) */
+int32_t cc_rng_seeded(const cc_handle *h);
 
 /* The baseline policies alone (greedy_policy.py:33-88, waiting_policy.py:33-72) on the
  * current state: actions_out [N,A] int8; agents that are done or inactive get CC_ACT_WAIT. */

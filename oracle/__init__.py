@@ -108,7 +108,8 @@ class OracleEnvs:
         if key not in self._out:
             n, a = self.n, self.a
             self._out[key] = dict(
-                obs=None if obs_dtype == _abi.OBS_NONE else np.zeros((n, a, self.obs_len), _OBS_NP[obs_dtype]),
+                obs=None if obs_dtype == _abi.OBS_NONE else (np.zeros((n, a, 4), np.int8) if obs_dtype == _abi.OBS_TABLE
+                                                             else np.zeros((n, a, self.obs_len), _OBS_NP[obs_dtype])),
                 reward=np.zeros((n, a), _REW_NP[reward_dtype]),
                 agent_flags=np.zeros((n, a), np.uint8),
                 agent_info=np.zeros((n, a), np.uint8),
@@ -179,7 +180,7 @@ class OracleEnvs:
         return out
 
     def observe(self, obs_dtype=_abi.OBS_INT8):
-        obs = np.zeros((self.n, self.a, self.obs_len), _OBS_NP[obs_dtype])
+        obs = np.zeros((self.n, self.a, 4), np.int8) if obs_dtype == _abi.OBS_TABLE else np.zeros((self.n, self.a, self.obs_len), _OBS_NP[obs_dtype])
         lib().cc_oracle_observe(C.byref(self.cfg), self.n, _ptr(self.x), _ptr(self.y), _ptr(self.flags),
                                 _ptr(self.step_count), _ptr(obs), obs_dtype)
         return obs

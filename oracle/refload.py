@@ -1,4 +1,5 @@
-"""Import the UNMODIFIED reference from ``/root/reference/src`` (build container only).
+"""Import the UNMODIFIED reference: from ``/root/reference/src`` in the build container, else from the archive
+``oracle/_ref/reference.zip`` that ``oracle/stage_ref.py`` stages there (git-ignored, travels with gpurun).
 
 gymnasium, ray and matplotlib are not installed and the hot path needs almost nothing from them
 (SURVEY.md §8c), so tiny stand-ins are injected into ``sys.modules`` first:
@@ -10,7 +11,7 @@ gymnasium, ray and matplotlib are not installed and the hot path needs almost no
 * ``ray.rllib.env.multi_agent_env.MultiAgentEnv`` is an ``Env`` with an empty ``__init__``;
 * ``matplotlib.pyplot`` only needs an ``Axes`` attribute (evaluated in a signature).
 
-Nothing here travels to the GPU box: ``available()`` is False there and every caller skips.
+Where neither the mount nor the archive exists ``available()`` is False and every caller skips.
 """
 
 from __future__ import annotations
@@ -21,12 +22,42 @@ from pathlib import Path
 
 import numpy as np
 
-REFERENCE_SRC = Path("/root/reference/src")
-REFERENCE_TESTS = Path("/root/reference/tests")
+ARCHIVE = Path(__file__).resolve().parent / "_ref" / "reference.zip"
+_MOUNT = Path("/root/reference")
+if (_MOUNT / "src" / "collectivecrossing" / "collectivecrossing.py").exists():
+    REFERENCE_SRC: Path | None = _MOUNT / "src"
+    REFERENCE_TESTS: Path | None = _MOUNT / "tests"
+    SOURCE = "mount"
+elif ARCHIVE.exists():
+    REFERENCE_SRC = ARCHIVE / "src"   # zipimport: a directory inside an archive is a valid sys.path entry
+    REFERENCE_TESTS = None            # extract_tests() unpacks them on demand
+    SOURCE = "archive"
+else:
+    REFERENCE_SRC = REFERENCE_TESTS = None
+    SOURCE = None
 
 
 def available() -> bool:
-    return (REFERENCE_SRC / "collectivecrossing" / "collectivecrossing.py").exists()
+    return REFERENCE_SRC is not None
+
+
+def extract(dest: Path, prefixes=("tests/", "src/", "scripts/", "examples/")) -> Path:
+    """Unpack the reference (mount or archive) under ``dest``; returns ``dest``."""
+    import shutil
+    import zipfile
+
+    dest = Path(dest)
+    if SOURCE == "mount":
+        for pre in prefixes:
+            src = _MOUNT / pre.rstrip("/")
+            if src.exists():
+                shutil.copytree(src, dest / pre.rstrip("/"), ignore=shutil.ignore_patterns("__pycache__"), dirs_exist_ok=True)
+    elif SOURCE == "archive":
+        with zipfile.ZipFile(ARCHIVE) as z:
+            z.extractall(dest, [n for n in z.namelist() if n.startswith(tuple(prefixes))])
+    else:
+        raise RuntimeError("reference neither mounted nor staged")
+    return dest
 
 
 def _install_stubs() -> None:
@@ -115,7 +146,7 @@ def load():
     if _ref is not None:
         return _ref
     if not available():
-        raise RuntimeError("reference sources are not mounted at /root/reference")
+        raise RuntimeError("reference sources are neither mounted at /root/reference nor staged at oracle/_ref/reference.zip")
     _install_stubs()
     if str(REFERENCE_SRC) not in sys.path:
         sys.path.insert(0, str(REFERENCE_SRC))
