@@ -192,30 +192,86 @@ def _py_worker(job):
     return steps, time.perf_counter() - t0
 
 
-def cpu_python_port(args, seconds, pool=None):
-    """The reference's own shape of computation: a pure-Python env + policy loop, one independent
-    env per host core (multiprocessing), reset() on episode end."""
+_REF_STATE = {}
+
+
+def _ref_worker(job):
+    """The UNMODIFIED reference (oracle/refload.py: /root/reference or the staged archive): its CollectiveCrossingEnv.step
+    (collectivecrossing.py:161-261) driven by its own GreedyPolicy / WaitingPolicy at epsilon 0 in the loop of
+    scripts/run_greedy_policy_demo.py:67-109, reset() on episode end."""
+    policy, seconds, seed = job
+    import logging
+
+    import numpy as np
+
+    logging.disable(logging.CRITICAL)   # the reference's policies log every construction
+    st = _REF_STATE
+    if "env" not in st:
+        from oracle import refload
+
+        ref = refload.load()
+        st["env"] = ref.CollectiveCrossingEnv(refload.to_reference_config(workload_config()))
+        st["policies"] = {"greedy": ref.GreedyPolicy(0.0, 42), "waiting": ref.WaitingPolicy(0.0, 42)}
+        st["obs"], _ = st["env"].reset(seed=seed)
+        st["term"] = {}
+    env, pol = st["env"], st["policies"].get(policy)
+    rng = np.random.default_rng(seed)
+    obs, terminateds = st["obs"], st["term"]
+    t0 = time.perf_counter()
+    steps = 0
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(20):
+            actions = {}
+            for agent_id in env.agents:                                   # run_greedy_policy_demo.py:71-77
+                if agent_id in obs and not terminateds.get(agent_id, False) and env._agents[agent_id].active:
+                    actions[agent_id] = pol.get_action(agent_id, obs[agent_id], env) if pol else int(rng.integers(0, 5))
+            obs, _, terminateds, truncateds, _ = env.step(actions)
+            steps += 1
+            if terminateds["__all__"] or truncateds["__all__"]:
+                obs, _ = env.reset()
+                terminateds = {}
+    st["obs"], st["term"] = obs, terminateds
+    return steps, time.perf_counter() - t0
+
+
+def reference_available() -> bool:
+    try:
+        from oracle import refload
+
+        return refload.available()
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def cpu_python_loop(args, seconds, pool=None):
+    """The reference's own shape of computation: a pure-Python env + policy loop, one independent env per host core
+    (multiprocessing), reset() on episode end.  The unmodified reference itself where it is available
+    (kind "reference"), else the oracle's Python port of the same loop (kind "port")."""
     import multiprocessing as mp
 
     cores = os.cpu_count() or 1
     own = pool is None
     if own:
         pool = mp.get_context("spawn").Pool(cores)
+    real = reference_available()
     try:
-        res = pool.map(_py_worker, [(args.policy, seconds, 1000 + k) for k in range(cores)])
+        res = pool.map(_ref_worker if real else _py_worker, [(args.policy, seconds, 1000 + k) for k in range(cores)])
     finally:
         if own:
             pool.close()
     rate = sum(s / dt for s, dt in res) * 8
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"pure-Python port of the reference loop (oracle/pyport.py), {cores} processes x 1 env, "
-                      f"{sum(s for s, _ in res)} env-steps in {seconds:.1f} s each, {args.policy} policy + step + reset on done"}
+    what = ("the unmodified reference (CollectiveCrossingEnv.step + its own baseline policy at epsilon 0, loop of "
+            "scripts/run_greedy_policy_demo.py:67-109; imported from the archive oracle/stage_ref.py stages)" if real
+            else "pure-Python port of the reference loop (oracle/pyport.py)")
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference" if real else "port",
+            "sample": f"{what}, {cores} processes x 1 env, {sum(s for s, _ in res)} env-steps in {seconds:.1f} s each, "
+                      f"{args.policy} policy + step + reset on done"}
 
 
 def run_reference(args):
-    """`--impl reference`: the reference is a pure-Python package that cannot travel to the GPU box
-    (tier rule), so its arm is the oracle's Python port of the same loop on all host cores.  A step
-    is a bounded sample: every core runs the loop for a fixed time slice."""
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores — the unmodified reference
+    where oracle/_ref holds its archive (or /root/reference is mounted), else the oracle's Python port.  A step is a bounded
+    sample: every core runs the loop for a fixed time slice."""
     import multiprocessing as mp
 
     rank = int(os.environ.get("RANK", "0"))
@@ -226,7 +282,7 @@ def run_reference(args):
     vals, info = [], None
     with mp.get_context("spawn").Pool(os.cpu_count() or 1) as pool:
         for k in range(total):
-            info = cpu_python_port(args, slice_s, pool)
+            info = cpu_python_loop(args, slice_s, pool)
             if k >= args.warmup:
                 vals.append(info["value"])
     value = sum(vals) / len(vals)

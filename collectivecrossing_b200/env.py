@@ -156,15 +156,19 @@ class CollectiveCrossingEnv(_Base):
             self.observation_space = self._observation_spaces[self._ids[0]]
 
     # ---- host view <-> device state ----------------------------------------------------------------
-    def _push_state(self, dev: Any = None, step_offset: int = 0) -> None:
-        """Upload the host records (tests and policies may have edited them) to the device."""
+    def _push_state(self, dev: Any = None, step_offset: int = 0, allow_unset: bool = False) -> None:
+        """Upload the host records (tests and policies may have edited them) to the device.  ``allow_unset``: agents
+        without a position yet (before the first reset) go to (0, 0) — the reference's truncation function is callable
+        then (tests/collectivecrossing/envs/test_truncateds.py:30-53) and does not look at positions."""
         dev = dev or self._dev
         A = len(self._ids)
         x, y, f = np.zeros((1, A), np.int8), np.zeros((1, A), np.int8), np.zeros((1, A), np.uint8)
         for k, a in enumerate(self._ids):
             ag = self._agents[a]
             if ag.position[0] is None:
-                raise RuntimeError("call reset() before step()")
+                if not allow_unset:
+                    raise RuntimeError("call reset() before step()")
+                continue
             x[0, k], y[0, k] = int(ag.position[0]), int(ag.position[1])
             f[0, k] = (_abi.F_ACTIVE if ag.active else 0) | (_abi.F_TERMINATED if ag.terminated else 0) | (_abi.F_TRUNCATED if ag.truncated else 0)
         dev.set_state(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(f),
@@ -266,7 +270,7 @@ class CollectiveCrossingEnv(_Base):
             cfg = self._config.model_copy(update=upd) if upd else self._config
             ev = self._evaluators[key] = BatchedCollectiveCrossing(cfg, 1, self._dev.device, obs_dtype="none", reward_dtype="float64",
                                                                    auto_reset=False)
-        self._push_state(ev, step_offset=-1)
+        self._push_state(ev, step_offset=-1, allow_unset=True)
         wait = torch.full((1, len(self._ids)), 4, dtype=torch.int8, device=ev.device)
         out = ev.step(wait)
         ev.check_error()

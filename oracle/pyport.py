@@ -149,6 +149,10 @@ class PyEnv:
         return obs, rewards, terminateds, truncateds, infos
 
     @property
+    def possible_agents(self):
+        return list(self.ids)
+
+    @property
     def agents(self):
         return [i for i in self.ids if not (self.term[i] or self.trunc[i])]
 

@@ -63,3 +63,50 @@ def test_pyport_replays_golden(name):
                 assert term[i] == bool(rec["agent_flags"][t, n, k] & 16)
                 if i in obs:
                     assert np.array_equal(obs[i], rec["obs"][t, n, k].astype(np.float32))
+
+
+def test_runner_shaped_sampling_loop_port_equals_reference():
+    """The env-runner-shaped sampling loop of tests/rllib_stub.py (used on the GPU against the façade) gives identical
+    episodes on the Python port and on the unmodified reference, driven through the reference's own
+    examples/training_script.py:26-64 (register_env + policy_mapping_fn + env_config, executed unchanged behind stub ray)."""
+    import sys
+    import tempfile
+    from pathlib import Path
+
+    import rllib_stub
+    from oracle import refload
+    from oracle.pyport import PyEnv
+
+    if not refload.available():
+        pytest.skip("reference neither mounted nor staged")
+    rllib_stub.install()
+    refload.load()
+    with tempfile.TemporaryDirectory() as d:
+        src = (refload.extract(Path(d), prefixes=("examples/",)) / "examples" / "training_script.py").read_text()
+    rllib_stub.ENV_REGISTRY.clear()
+    ns = rllib_stub.run_training_script_head(src)
+    theirs = rllib_stub.ENV_REGISTRY["collective_crossing"](ns["env_config"])
+    assert type(theirs).__module__ == "collectivecrossing.collectivecrossing"
+    from collectivecrossing_b200.configs import CollectiveCrossingConfig
+    ours_cfg = CollectiveCrossingConfig(**{k: (type(v).__name__, v.model_dump()) if hasattr(v, "model_dump") else v for k, v in ns["env_config"].items()
+                                           if not hasattr(v, "model_dump")},
+                                        **_own_strategy_configs(ns["env_config"]))
+    policies = {"boarding": rllib_stub.SeededPolicy(1), "exiting": rllib_stub.SeededPolicy(2)}
+    want = rllib_stub.sample_episodes(theirs, ns["policy_mapping_fn"], policies, n_steps=250, seed=11)
+    got = rllib_stub.sample_episodes(PyEnv(ours_cfg), ns["policy_mapping_fn"], policies, n_steps=250, seed=11)
+    assert len(want) >= 2
+    rllib_stub.assert_same_episodes(got, want, "python port vs reference")
+
+
+def _own_strategy_configs(env_config: dict) -> dict:
+    """The reference's strategy config objects of an env_config dict rebuilt as OUR classes (same names, same fields)."""
+    import collectivecrossing_b200.reward_configs as rc
+    import collectivecrossing_b200.terminated_configs as tc
+    import collectivecrossing_b200.truncated_configs as uc
+
+    out = {}
+    for key, mod in (("reward_config", rc), ("terminated_config", tc), ("truncated_config", uc)):
+        if key in env_config:
+            v = env_config[key]
+            out[key] = getattr(mod, type(v).__name__)(**v.model_dump())
+    return out
