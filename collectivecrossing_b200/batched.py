@@ -148,6 +148,11 @@ class BatchedCollectiveCrossing:
         code = int(self._lib.cc_last_kernel_variant(self._h))
         return {0: "none", 1: "lanes", 2: "threads"}[code]
 
+    @property
+    def last_kernel_name(self) -> str:
+        """Instantiation the last ``step`` launch ran, e.g. ``ccb::cc_step_tpe_kernel<8,4>``."""
+        return self._lib.cc_last_kernel_name(self._h).decode()
+
     # ------------------------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None):

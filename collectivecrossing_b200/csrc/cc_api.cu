@@ -665,6 +665,7 @@ int cc_set_kernel_variant(cc_handle *h, int32_t variant) {
     return CC_OK;
 }
 int32_t cc_last_kernel_variant(const cc_handle *h) { return h ? h->last_variant : 0; }
+const char *cc_last_kernel_name(const cc_handle *h) { return h ? h->last_kernel : ""; }
 
 int cc_timing_begin(cc_handle *h, void *stream) {
     if (!h) return cc_fail(CC_ERR_INVALID_ARG, "null handle");

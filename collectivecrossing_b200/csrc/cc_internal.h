@@ -53,6 +53,7 @@ struct cc_handle {
     int64_t tpe_launches = 0;
     int variant = CC_KERNEL_AUTO;   // cc_set_kernel_variant
     int last_variant = 0;           // mapping of the last step launch (CC_KERNEL_LANES / CC_KERNEL_THREADS)
+    char last_kernel[64] = "";      // name of the last step kernel launched (cc_last_kernel_name)
     std::vector<cc_launch_cfg> launch_cfgs;
     // stream order (header, "Stream order"): recorded behind every stream-taking call, awaited by the host path
     cudaEvent_t ev_order = nullptr;

@@ -55,8 +55,13 @@ struct T2Layout {
 };
 
 // 0xFFFFFFFF if bit 7 of byte k of w is set, else 0 (PRMT with the sign-replicate selector)
-template <int K>
-__device__ __forceinline__ unsigned t2_fill(unsigned w) { return __byte_perm(w, 0u, 0x8888u | (K * 0x1111u)); }
+// (k is a constant after unrolling: the selector is an immediate)
+// (inline PTX: the __byte_perm intrinsic documents only the 3 index bits of a selector nibble)
+__device__ __forceinline__ unsigned t2_fill(unsigned w, int k) {
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "r"(0x8888u | ((unsigned)k * 0x1111u)));
+    return r;
+}
 // bytes B of a, b, c, d -> one word (a in byte 0)
 template <int B>
 __device__ __forceinline__ unsigned t2_gather4(unsigned a, unsigned b, unsigned c, unsigned d) {
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                 const unsigned vmask = (e[k].x >> 24) & 15u & ~occ;
                 unsigned a;
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(a) : "r"(act_s + (((e[k].x & 31u) << 4) | vmask)));
-                const unsigned m = k < 4 ? t2_fill<(k & 3)>(go7[0]) : t2_fill<(k & 3)>(go7[1]);
+                const unsigned m = t2_fill(k < 4 ? go7[0] : go7[1], k & 3);
                 act[k] = ((a ^ (unsigned)CC_ACT_WAIT) & m) ^ (unsigned)CC_ACT_WAIT;
             }
             geo_known = true;
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
             unsigned cmp[A], am[A];
 #pragma unroll
             for (int k = 0; k < A; ++k) {
-                am[k] = k < 4 ? t2_fill<(k & 3)>(act7_0) : t2_fill<(k & 3)>(act7_1);
+                am[k] = t2_fill(k < 4 ? act7_0 : act7_1, k & 3);
                 cmp[k] = c[k] | ~am[k];
             }
 #pragma unroll
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
         {
             const unsigned a7_0 = alive0 << 7, a7_1 = alive1 << 7;
 #pragma unroll
-            for (int k = 0; k < A; ++k) rew[k] = __uint_as_float(e[k].y & (k < 4 ? t2_fill<(k & 3)>(a7_0) : t2_fill<(k & 3)>(a7_1)));
+            for (int k = 0; k < A; ++k) rew[k] = __uint_as_float(e[k].y & (t2_fill(k < 4 ? a7_0 : a7_1, k & 3)));
         }
         // reward sum of the env: the balanced float32 tree the other kernels and the oracle use
         float rsum;

@@ -1,6 +1,8 @@
 // cc_launch_lanes.cu — instantiations and launcher of ccb::cc_kernel (one lane per agent, cc_kernels.cuh) and of the
 // numpy-exact seeded reset kernel.  Host-side plumbing only.
 #define CCB_WITH_RESET_SEEDED 1
+#include <cstdio>
+
 #include "cc_internal.h"
 #include "cc_kernels.cuh"
 
@@ -23,6 +25,7 @@ int launch_t(cc_handle *h, const KParams &p, cudaStream_t s) {
     if (grid < 1) grid = 1;
     kern<<<grid, ccb::kThreads, smem, s>>>(p);
     CC_CUDA(cudaGetLastError());
+    if (MODE == ccb::kModeStep) snprintf(h->last_kernel, sizeof h->last_kernel, "ccb::cc_kernel<%d,%d,%d,step>", LPE, APL, OBS);
     h->launches += 1;
     return CC_OK;
 }

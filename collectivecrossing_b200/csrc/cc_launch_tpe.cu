@@ -1,7 +1,10 @@
 // cc_launch_tpe.cu — instantiations and launcher of ccb::cc_step_tpe_kernel (one thread per env, cc_kernel_tpe.cuh).
 // Host-side plumbing only.  CCB_TPE_PART (0 / 1) splits the crews over two objects so that they compile in parallel.
+#include <cstdio>
+#include <cstdlib>
+
 #include "cc_internal.h"
-#include "cc_kernel_tpe.cuh"
+#include "cc_kernel_tpe2.cuh"
 
 #ifndef CCB_TPE_PART
 #error "compile with -DCCB_TPE_PART=0 (crews 1-4 and 8-agent int8 rows) or 1 (crews 5-8)"
@@ -40,13 +43,50 @@ int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
     if (grid < 1) grid = 1;
     kern<<<grid, ccb::kTpeThreads, smem, s>>>(p);
     CC_CUDA(cudaGetLastError());
+    snprintf(h->last_kernel, sizeof h->last_kernel, "ccb::cc_step_tpe_kernel<%d,%d>", A, OBS);
     h->launches += 1;
     h->tpe_launches += 1;
     return CC_OK;
 }
 
+// cc_step_tpe2_kernel: small lattices, compact output modes (cc_kernel_tpe2.cuh)
+template <int A, int OBS>
+int launch_tpe2_t(cc_handle *h, KParams p, cudaStream_t s) {
+    using L = ccb::T2Layout<A, OBS>;
+    auto kern = ccb::cc_step_tpe2_kernel<A, OBS>;
+    p.n_groups = (p.n_envs + 31) / 32;
+    if (p.n_steps < 1) p.n_steps = 1;
+    p.tpe_counter = h->tpe_counters + (h->tpe_launches & 1);
+    p.tpe_counter_next = h->tpe_counters + ((h->tpe_launches + 1) & 1);
+    const int smem = L::kDynBytes;
+    int per_sm = 0;
+    int rc = cc_cached_occupancy(h, reinterpret_cast<const void *>(kern), ccb::kT2Threads, smem, &per_sm);
+    if (rc != CC_OK) return rc;
+    long long want = (p.n_groups + ccb::kT2Warps - 1) / ccb::kT2Warps;
+    long long cap = (long long)h->sm_count * per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, ccb::kT2Threads, smem, s>>>(p);
+    CC_CUDA(cudaGetLastError());
+    snprintf(h->last_kernel, sizeof h->last_kernel, "ccb::cc_step_tpe2_kernel<%d,%d>", A, OBS);
+    h->launches += 1;
+    h->tpe_launches += 1;
+    return CC_OK;
+}
+
+// the small-lattice kernel serves: padded lattice of at most 256 cells, 32 columns, 16 rows; no float32 rows.
+// CCB200_TPE2=0 in the environment switches it off (A/B measurements).
+bool tpe2_eligible(const KParams &p, int obs_dtype) {
+    static const bool enabled = [] { const char *v = std::getenv("CCB200_TPE2"); return !(v && v[0] == '0'); }();
+    const int PW = p.W + 3, PH = p.H + 3;
+    return enabled && obs_dtype != CC_OBS_FP32 && PW <= ccb::kT2MaxCols && PH <= ccb::kT2MaxRows && PW * PH <= ccb::kT2MaxCells;
+}
+
 }  // namespace
 
+#define CCB_TPE2_CASES(A_)                                                                  \
+    case A_ * 32 + CC_OBS_NONE: return launch_tpe2_t<A_, CC_OBS_NONE>(h, p, s);                 \
+    case A_ * 32 + CC_OBS_TABLE: return launch_tpe2_t<A_, CC_OBS_TABLE>(h, p, s);
 #define CCB_TPE_CASES(A_)                                                                   \
     case A_ * 32 + CC_OBS_NONE: return launch_tpe_t<A_, CC_OBS_NONE>(h, p, s);                  \
     case A_ * 32 + CC_OBS_TABLE: return launch_tpe_t<A_, CC_OBS_TABLE>(h, p, s);                \
@@ -54,6 +94,9 @@ int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
 
 #if CCB_TPE_PART == 0
 int cc_launch_tpe_part0(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s) {
+    if (tpe2_eligible(p, obs_dtype)) {
+        switch (p.A * 32 + obs_dtype) { CCB_TPE2_CASES(1) CCB_TPE2_CASES(2) CCB_TPE2_CASES(3) CCB_TPE2_CASES(4) }
+    }
     switch (p.A * 32 + obs_dtype) {
         CCB_TPE_CASES(1) CCB_TPE_CASES(2) CCB_TPE_CASES(3) CCB_TPE_CASES(4)
     case 8 * 32 + CC_OBS_INT8: return launch_tpe_t<8, CC_OBS_INT8>(h, p, s);
@@ -63,6 +106,12 @@ int cc_launch_tpe_part0(cc_handle *h, const KParams &p, int obs_dtype, cudaStrea
 #else
 int cc_launch_tpe_part0(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s);
 int cc_launch_tpe(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s) {
+    if (tpe2_eligible(p, obs_dtype)) {
+        switch (p.A * 32 + obs_dtype) {
+            CCB_TPE2_CASES(5) CCB_TPE2_CASES(6) CCB_TPE2_CASES(7) CCB_TPE2_CASES(8)
+        case 8 * 32 + CC_OBS_INT8: return launch_tpe2_t<8, CC_OBS_INT8>(h, p, s);
+        }
+    }
     switch (p.A * 32 + obs_dtype) {
         CCB_TPE_CASES(5) CCB_TPE_CASES(6) CCB_TPE_CASES(7) CCB_TPE_CASES(8)
     }

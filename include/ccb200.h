@@ -298,6 +298,9 @@ int64_t cc_launch_count(const cc_handle *h);
 enum { CC_KERNEL_AUTO = 0, CC_KERNEL_LANES = 1, CC_KERNEL_THREADS = 2 };
 int cc_set_kernel_variant(cc_handle *h, int32_t variant);
 int32_t cc_last_kernel_variant(const cc_handle *h); /* mapping of the last cc_step launch (0 = none yet) */
+/* instantiation the last step launch ran, e.g. "ccb::cc_step_tpe_kernel<8,4>" (float32 rows), "ccb::cc_step_tpe2_kernel<8,1>"
+ * (the small-lattice kernel of the compact modes) or "ccb::cc_kernel<32,2,1,step>"; "" before the first launch */
+const char *cc_last_kernel_name(const cc_handle *h);
 /* average device time (ms) of the step kernel launches bracketed by cc_timing_begin/_end,
  * measured with CUDA events on the launching stream */
 int cc_timing_begin(cc_handle *h, void *stream);
