@@ -444,6 +444,7 @@ void cc_destroy(cc_handle *h) {
     if (h->host_table) cudaFreeHost(h->host_table);
     for (cudaEvent_t ev : h->ev_chunk) cudaEventDestroy(ev);
     if (h->gen) cudaFree(h->gen);
+    if (h->t2_tables) cudaFree(h->t2_tables);
     for (cudaStream_t s : {h->s_in, h->s_k, h->s_out})
         if (s) cudaStreamDestroy(s);
     for (int i = 0; i < cc_handle::kRing; ++i)

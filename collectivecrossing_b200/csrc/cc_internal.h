@@ -55,6 +55,7 @@ struct cc_handle {
     int last_variant = 0;           // mapping of the last step launch (CC_KERNEL_LANES / CC_KERNEL_THREADS)
     char last_kernel[64] = "";      // name of the last step kernel launched (cc_last_kernel_name)
     std::vector<cc_launch_cfg> launch_cfgs;
+    void *t2_tables = nullptr;      // tables of the small-lattice kernel (built on first use; the config is immutable)
     // stream order (header, "Stream order"): recorded behind every stream-taking call, awaited by the host path
     cudaEvent_t ev_order = nullptr;
     bool order_pending = false;
@@ -83,3 +84,5 @@ int cc_launch_tpe(cc_handle *h, const ccb::KParams &p, int obs_dtype, cudaStream
 // cc_reset_seeded_kernel (numpy-exact PCG64 placement), in cc_launch_lanes.cu
 int cc_launch_reset_seeded(cc_handle *h, const ccb::KParams &p, const int64_t *seeds, cudaStream_t s);
 size_t cc_rng_state_bytes(void);   // sizeof(ccb::Pcg64State)
+// cc_launch_tpe.cu (part 1): h->t2_tables, built by one block on stream s the first time
+int cc_t2_ensure_tables(cc_handle *h, const ccb::KParams &p, cudaStream_t s);

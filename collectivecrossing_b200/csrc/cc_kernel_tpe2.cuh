@@ -44,6 +44,14 @@ constexpr int kT2BitmapBytesPerWarp = kT2MaxRows * 128;   // row r of lane l at 
 //           bit 4 the cell itself is a valid position, bit 5 the cell is excluded from boarding spawns (:110-115)
 enum { kT2InTram = 1u << 5, kT2AtDoor = 1u << 6, kT2Arrived = 1u << 7, kT2Valid = 1u << 28, kT2SpawnExcluded = 1u << 29 };
 
+// The tables of one config, built once per handle by cc_t2_tables_kernel and copied into shared memory by every CTA.
+struct T2Tables {
+    uint2 tab[2 * kT2MaxCells];            // [cell][type] {geo, reward}
+    uint8_t act2[kPolicyRows * 16];        // greedy decision by (table row, free-neighbour mask in bitmap order)
+    int dcell[8];                          // cell delta of actions 0..3 (actions.py:18-24); 0 for wait / invalid
+};
+static_assert(sizeof(T2Tables) % 16 == 0, "copied as 16-byte vectors");
+
 template <int A, int OBS>
 struct T2Layout {
     static constexpr bool kImage = OBS == CC_OBS_INT8;                 // 8 agents: an env's block is 19 x 16 bytes
@@ -92,25 +100,14 @@ __device__ __forceinline__ void t2_store_packed(void *base, int env, unsigned w0
     }
 }
 
-template <int A, int OBS>
-__global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_kernel(const __grid_constant__ KParams p) {
-    using L = T2Layout<A, OBS>;
-    static_assert(A >= 1 && A <= 8, "thread-per-env mapping is for crews of at most 8");
-    static_assert(OBS == CC_OBS_NONE || OBS == CC_OBS_TABLE || (OBS == CC_OBS_INT8 && A == 8), "float32 rows: cc_step_tpe_kernel");
-    constexpr unsigned kOnes = 0x01010101u;
-    // byte lanes of the agents that exist (k < A)
-    constexpr unsigned kM0 = A >= 4 ? kOnes : (kOnes >> (8 * (4 - A)));
-    constexpr unsigned kM1 = A <= 4 ? 0u : (A == 8 ? kOnes : (kOnes >> (8 * (8 - A))));
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ uint2 tab[2 * kT2MaxCells];          // [cell][type] {geo, reward}
-    __shared__ uint8_t act2[kPolicyRows * 16];      // greedy decision by (table row, free-neighbour mask in bitmap order)
-    __shared__ int dcell[8];                        // cell delta of actions 0..3 (actions.py:18-24); 0 for wait / invalid
-    __shared__ unsigned long long red_all[kT2Warps * kStCount];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// one block: the tables of a config (collectivecrossing.py:509-563, rewards.py:41-182, greedy_policy.py:64-449 per cell)
+// (a plain function, not a template: defined in the one translation unit that sets CCB_WITH_T2_TABLES)
+#ifdef CCB_WITH_T2_TABLES
+__global__ void __launch_bounds__(256) cc_t2_tables_kernel(const __grid_constant__ KParams p, T2Tables *out) {
     const int PW = p.W + 3, PH = p.H + 3;
-
-    // ---- once per CTA: the tables --------------------------------------------------------------------------------
+    uint2 *tab = out->tab;
+    uint8_t *act2 = out->act2;
+    int *dcell = out->dcell;
     for (int i = threadIdx.x; i < 2 * kT2MaxCells; i += blockDim.x) {
         const int cell = i >> 1, type = i & 1;
         const int yy = cell / PW - 1, xx = cell - (yy + 1) * PW - 1;
@@ -148,23 +145,49 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
         act2[i] = (uint8_t)greedy_decision(i >> 4, ((m >> 2) & 1u) | (m & 2u) | ((m & 1u) << 2) | (m & 8u));
     }
     if (threadIdx.x < 8) dcell[threadIdx.x] = threadIdx.x == 0 ? 1 : (threadIdx.x == 1 ? PW : (threadIdx.x == 2 ? -1 : (threadIdx.x == 3 ? -PW : 0)));
+}
+#endif  // CCB_WITH_T2_TABLES
+
+// BT >= 0: the number of boarding agents is known at compile time (the README crew, 5 + 3: the type of agent k and with it
+// the table half it reads, the boarding / exiting byte masks ... are immediates); BT = -1: any crew (p.B).
+template <int A, int OBS, int BT>
+__global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_kernel(const __grid_constant__ KParams p) {
+    using L = T2Layout<A, OBS>;
+    const int B = BT >= 0 ? BT : p.B;
+    static_assert(A >= 1 && A <= 8, "thread-per-env mapping is for crews of at most 8");
+    static_assert(OBS == CC_OBS_NONE || OBS == CC_OBS_TABLE || (OBS == CC_OBS_INT8 && A == 8), "float32 rows: cc_step_tpe_kernel");
+    constexpr unsigned kOnes = 0x01010101u;
+    // byte lanes of the agents that exist (k < A)
+    constexpr unsigned kM0 = A >= 4 ? kOnes : (kOnes >> (8 * (4 - A)));
+    constexpr unsigned kM1 = A <= 4 ? 0u : (A == 8 ? kOnes : (kOnes >> (8 * (8 - A))));
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(16) T2Tables tb;
+    __shared__ unsigned long long red_all[kT2Warps * kStCount];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int PW = p.W + 3, PH = p.H + 3;
+
+    // ---- once per CTA: the tables (L2-resident, 4.7 KB) and a clean bitmap ------------------------------------------
+    for (int i = threadIdx.x; i < (int)(sizeof(T2Tables) / 16); i += blockDim.x)
+        reinterpret_cast<uint4 *>(&tb)[i] = static_cast<const uint4 *>(p.t2_tables)[i];
+    for (int i = threadIdx.x; i < L::kDynBytes / 4; i += blockDim.x) reinterpret_cast<unsigned *>(smem)[i] = 0u;
     unsigned long long *red = red_all + warp * kStCount;
     if (lane < kStCount) red[lane] = 0ull;
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.tpe_counter_next = 0u;   // the counter the NEXT launch uses
     __syncthreads();
 
-    const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab), act_s = (unsigned)__cvta_generic_to_shared(act2),
-                   dc_s = (unsigned)__cvta_generic_to_shared(dcell);
+    const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tb.tab), act_s = (unsigned)__cvta_generic_to_shared(tb.act2),
+                   dc_s = (unsigned)__cvta_generic_to_shared(tb.dcell);
     unsigned char *wsmem = smem + warp * L::kBytesPerWarp;
     const unsigned img_s = (unsigned)__cvta_generic_to_shared(wsmem);
     const unsigned bm = img_s + 4u * lane;                      // this thread's bitmap row r at bm + 128 r
     unsigned tbase[A];                                          // table base of agent k's type
 #pragma unroll
-    for (int k = 0; k < A; ++k) tbase[k] = tab_s + (k < p.B ? 0u : 8u);
+    for (int k = 0; k < A; ++k) tbase[k] = tab_s + (k < B ? 0u : 8u);
     // bytes 0x01 of the boarding agents; destination test and type byte are in the table
     unsigned boardw[2];
-    boardw[0] = (p.B >= 4 ? kOnes : (p.B <= 0 ? 0u : (kOnes >> (8 * (4 - p.B))))) & kM0;
-    boardw[1] = (p.B <= 4 ? 0u : (p.B >= 8 ? kOnes : (kOnes >> (8 * (8 - p.B))))) & kM1;
+    boardw[0] = (B >= 4 ? kOnes : (B <= 0 ? 0u : (kOnes >> (8 * (4 - B))))) & kM0;
+    boardw[1] = (B <= 4 ? 0u : (B >= 8 ? kOnes : (kOnes >> (8 * (8 - B))))) & kM1;
     const unsigned typew0 = kM0 & ~boardw[0], typew1 = kM1 & ~boardw[1];   // observations.py:86: 0 boarding, 1 exiting
 
     auto lookup = [&](unsigned c, int k) {
@@ -239,14 +262,18 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
             }
+            // (the bitmap is clean: zeroed at kernel start and after every use; where it aliases the image, zeroed here)
+            if constexpr (L::kImage) {
 #pragma unroll
-            for (int r = 0; r < kT2MaxRows; ++r)
-                if (r < PH) sts32(bm + 128u * r, 0u);
+                for (int r = 0; r < kT2MaxRows; ++r)
+                    if (r < PH) sts32(bm + 128u * r, 0u);
+            }
             unsigned arow[A];
 #pragma unroll
             for (int k = 0; k < A; ++k) {
                 arow[k] = bm + 128u + ((e[k].x >> 9) & 0x780u);                       // row y + 1
-                if ((fl[k >> 2] >> (8 * (k & 3))) & 1u) sts32(arow[k], lds32(arow[k]) | (2u << ((e[k].x >> 8) & 31u)));   // column x + 1
+                if ((fl[k >> 2] >> (8 * (k & 3))) & 1u)                               // column x + 1
+                    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(arow[k]), "r"(2u << ((e[k].x >> 8) & 31u)) : "memory");
             }
             // waiting_policy.py:118-131: some exiting agent that is not done has not arrived
             const unsigned nd0 = ~((fl[0] >> 1) | (fl[0] >> 2)) & m0e, nd1 = ~((fl[1] >> 1) | (fl[1] >> 2)) & m1e;
@@ -267,6 +294,11 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(a) : "r"(act_s + (((e[k].x & 31u) << 4) | vmask)));
                 const unsigned m = t2_fill(k < 4 ? go7[0] : go7[1], k & 3);
                 act[k] = ((a ^ (unsigned)CC_ACT_WAIT) & m) ^ (unsigned)CC_ACT_WAIT;
+            }
+            if constexpr (!L::kImage) {
+#pragma unroll
+                for (int k = 0; k < A; ++k)
+                    if ((fl[k >> 2] >> (8 * (k & 3))) & 1u) sts32(arow[k], 0u);
             }
             geo_known = true;
         }
@@ -292,16 +324,32 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                 am[k] = t2_fill(k < 4 ? act7_0 : act7_1, k & 3);
                 cmp[k] = c[k] | ~am[k];
             }
-#pragma unroll
-            for (int k = 0; k < A; ++k) {
-                int d;
-                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(d) : "r"(dc_s + act[k] * 4u));
-                if (!geo_known) d = ((e[k].x >> (20u + act[k])) & 1u) ? d : 0;          // :509-534 through the table (wait: bit 4 is 0... see below)
+            // one agent's turn: the target is committed unless some cmp value equals it — a chain of setp.eq.or on ONE predicate
+            // (the compiler's own rendering of the same test is a compare + select per pair)
+            auto turn = [&](const int k, const int d) {
                 const unsigned target = (c[k] + (unsigned)d) | ~am[k];
-                bool hit = false;
+                auto cm = [&](int j) { return cmp[j < A ? j : 0]; };
+                asm("{\n\t.reg .pred q;\n\t"
+                    "setp.eq.u32 q, %1, %9;\n\tsetp.eq.or.u32 q, %2, %9, q;\n\tsetp.eq.or.u32 q, %3, %9, q;\n\tsetp.eq.or.u32 q, %4, %9, q;\n\t"
+                    "setp.eq.or.u32 q, %5, %9, q;\n\tsetp.eq.or.u32 q, %6, %9, q;\n\tsetp.eq.or.u32 q, %7, %9, q;\n\tsetp.eq.or.u32 q, %8, %9, q;\n\t"
+                    "selp.u32 %0, %10, %9, q;\n\t}"                                           // :406-408
+                    : "=r"(cmp[k]) : "r"(cm(0)), "r"(cm(1)), "r"(cm(2)), "r"(cm(3)), "r"(cm(4)), "r"(cm(5)), "r"(cm(6)), "r"(cm(7)), "r"(target), "r"(cmp[k]));
+            };
+            if (geo_known) {
 #pragma unroll
-                for (int j = 0; j < A; ++j) hit |= cmp[j] == target;
-                if (!hit) cmp[k] = target;                                              // :406-408
+                for (int k = 0; k < A; ++k) {
+                    int d;
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(d) : "r"(dc_s + act[k] * 4u));
+                    turn(k, d);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    int d;
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(d) : "r"(dc_s + act[k] * 4u));
+                    d = ((e[k].x >> (20u + act[k])) & 1u) ? d : 0;   // :509-534 through the table (wait / invalid: d is 0 already)
+                    turn(k, d);
+                }
             }
 #pragma unroll
             for (int k = 0; k < A; ++k) c[k] = (cmp[k] & am[k]) | (c[k] & ~am[k]);      // ghosts never move
@@ -396,11 +444,11 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                 for (int attempt = 0; attempt < kResetAttemptCap && !ok; ++attempt) {
                     const U4 r = draw_at(p, t_rng, genv, kStreamReset, ((unsigned)i << 16) | (unsigned)attempt);
                     int cx, cy;
-                    if (i < p.B) { cx = bounded(r.v0, p.W); cy = bounded(r.v1, p.D); }                                   // :103-117
+                    if (i < B) { cx = bounded(r.v0, p.W); cy = bounded(r.v1, p.D); }                                   // :103-117
                     else { cx = p.TL + bounded(r.v0, p.TR + 1 - p.TL); cy = p.D + bounded(r.v1, p.H - p.D); }            // :132-140
                     cand = (unsigned)((cy + 1) * PW + cx + 1);
-                    const unsigned ge = tab[(cand & 255u) * 2].x;
-                    ok = (ge & kT2Valid) && !(i < p.B && (ge & kT2SpawnExcluded));
+                    const unsigned ge = tb.tab[(cand & 255u) * 2].x;
+                    ok = (ge & kT2Valid) && !(i < B && (ge & kT2SpawnExcluded));
 #pragma unroll
                     for (int j = 0; j < i; ++j) ok = ok && c[j] != cand;
                 }

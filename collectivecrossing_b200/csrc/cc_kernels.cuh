@@ -82,6 +82,7 @@ struct KParams {
     int nvec_env;                 // 16-byte vectors of an env's observation block
     long long obs_env_offset;     // lane-group kernel: the observation rows of env n go to row block n + obs_env_offset of p.obs
     int n_steps;                  // env-steps per env in this launch (1 for cc_step)
+    const void *t2_tables;        // small-lattice kernel: its tables, built once per handle (cc_kernel_tpe2.cuh: T2Tables)
     long long slice_agents;       // elements of one time slice of a per-agent array: n_envs * A
     long long slice_envs;         // ... of a per-env array: n_envs
     long long slice_obs_bytes;    // ... of the observation tensor, in bytes

@@ -3,6 +3,9 @@
 #include <cstdio>
 #include <cstdlib>
 
+#if CCB_TPE_PART == 1
+#define CCB_WITH_T2_TABLES 1
+#endif
 #include "cc_internal.h"
 #include "cc_kernel_tpe2.cuh"
 
@@ -50,10 +53,13 @@ int launch_tpe_t(cc_handle *h, KParams p, cudaStream_t s) {
 }
 
 // cc_step_tpe2_kernel: small lattices, compact output modes (cc_kernel_tpe2.cuh)
-template <int A, int OBS>
+template <int A, int OBS, int BT = -1>
 int launch_tpe2_t(cc_handle *h, KParams p, cudaStream_t s) {
     using L = ccb::T2Layout<A, OBS>;
-    auto kern = ccb::cc_step_tpe2_kernel<A, OBS>;
+    auto kern = ccb::cc_step_tpe2_kernel<A, OBS, BT>;
+    int rc0 = cc_t2_ensure_tables(h, p, s);
+    if (rc0 != CC_OK) return rc0;
+    p.t2_tables = h->t2_tables;
     p.n_groups = (p.n_envs + 31) / 32;
     if (p.n_steps < 1) p.n_steps = 1;
     p.tpe_counter = h->tpe_counters + (h->tpe_launches & 1);
@@ -105,8 +111,27 @@ int cc_launch_tpe_part0(cc_handle *h, const KParams &p, int obs_dtype, cudaStrea
 }
 #else
 int cc_launch_tpe_part0(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s);
+int cc_t2_ensure_tables(cc_handle *h, const KParams &p, cudaStream_t s) {
+    if (h->t2_tables) return CC_OK;
+    void *buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, sizeof(ccb::T2Tables));
+    if (e != cudaSuccess) return cc_fail(CC_ERR_NOMEM, "cudaMalloc for the small-lattice tables: %s", cudaGetErrorString(e));
+    ccb::cc_t2_tables_kernel<<<1, 256, 0, s>>>(p, static_cast<ccb::T2Tables *>(buf));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(buf); return cc_fail(CC_ERR_CUDA, "cc_t2_tables_kernel: %s", cudaGetErrorString(e)); }
+    h->t2_tables = buf;   // (a one-time set-up launch: not counted in cc_launch_count)
+    return CC_OK;
+}
+
 int cc_launch_tpe(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s) {
     if (tpe2_eligible(p, obs_dtype)) {
+        if (p.A == 8 && p.B == 5) {   // the README crew: boarding / exiting split known at compile time
+            switch (obs_dtype) {
+            case CC_OBS_NONE: return launch_tpe2_t<8, CC_OBS_NONE, 5>(h, p, s);
+            case CC_OBS_TABLE: return launch_tpe2_t<8, CC_OBS_TABLE, 5>(h, p, s);
+            case CC_OBS_INT8: return launch_tpe2_t<8, CC_OBS_INT8, 5>(h, p, s);
+            }
+        }
         switch (p.A * 32 + obs_dtype) {
             CCB_TPE2_CASES(5) CCB_TPE2_CASES(6) CCB_TPE2_CASES(7) CCB_TPE2_CASES(8)
         case 8 * 32 + CC_OBS_INT8: return launch_tpe2_t<8, CC_OBS_INT8>(h, p, s);
