@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--policy", default="greedy", choices=["greedy", "waiting", "random"])
     ap.add_argument("--steps-per-launch", type=int, default=20,
                     help="env-steps fused into one launch (cc_rollout_fused); 1 = one launch per step")
+    ap.add_argument("--reps", type=int, default=5, help="repetitions of the timed region (the median is reported)")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
@@ -300,20 +301,28 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def time_steps(env, torch, dist, args, steps, policy, world, per_launch=1):
-    """EXACTLY `steps` env-steps of every env: steps // per_launch fused launches of `per_launch` steps
-    (all of whose observations, rewards and flags are written) and steps % per_launch single-step launches."""
+def time_steps(env, torch, dist, args, steps, policy, world, per_launch=1, sharded=None):
+    """ONE timed region: EXACTLY `steps` env-steps of every env — steps // per_launch fused launches of `per_launch` steps
+    (all of whose observations, rewards and flags are written) and steps % per_launch single-step launches — bracketed by
+    barrier + synchronize, CUDA events on the launching stream, max over ranks.  With `sharded` (world > 1) the episode
+    statistics are all-reduced (NCCL) once per launch INSIDE the region, enqueued behind the kernels with no host wait.
+    Returns (ms, reduced statistics tensor or None)."""
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats_t = None
     e0.record()
     if per_launch > 1:
         for _ in range(steps // per_launch):
             env.rollout_trajectory(per_launch, policy=policy)
+            if sharded is not None:
+                stats_t = sharded.global_stats_device()
         steps = steps % per_launch
     for _ in range(steps):
         env.step(policy=policy)
+        if sharded is not None:
+            stats_t = sharded.global_stats_device()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -322,7 +331,12 @@ def time_steps(env, torch, dist, args, steps, policy, world, per_launch=1):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
-    return ms
+    return ms, stats_t
+
+
+def median(vals):
+    v = sorted(vals)
+    return v[len(v) // 2] if len(v) % 2 else 0.5 * (v[len(v) // 2 - 1] + v[len(v) // 2])
 
 
 def bind_to_gpu_numa_node(gpu_index: int):
@@ -346,10 +360,70 @@ def bind_to_gpu_numa_node(gpu_index: int):
         return None
 
 
+def host_copy_bandwidth(torch):
+    """Host-memory copy bandwidth with every host thread (torch CPU copy of 1 GiB): context for the host-buffer path."""
+    try:
+        a = torch.ones(1 << 28, dtype=torch.float32)
+        b = torch.empty_like(a)
+        b.copy_(a)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            b.copy_(a)
+        return 3 * 2 * a.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def time_e2e(env, torch, dist, world, policy, steps, host, T=1, on_device_policy=False):
+    """The host-buffer path a numpy / RLlib caller binds, timed by wall clock AND CUDA events (the larger counts), max over
+    ranks: per step the actions come from HOST memory (pinned) and every output lands in HOST memory (cc_step_host); with
+    T > 1 one cc_rollout_host call rolls T steps out with the on-device policy.  Returns ms per env-step."""
+    n, A = env.num_envs, env.num_agents
+    dev_actions = torch.zeros((n, A), dtype=torch.int8, device=env.device)
+
+    def one():
+        if T > 1:
+            env.rollout_host(host, T, policy=policy)
+        elif on_device_policy:
+            env.step_host(host, policy=policy)
+        else:
+            env.policy_actions(policy, out=dev_actions)            # stands in for the caller's host-side policy ...
+            host["actions"].copy_(dev_actions, non_blocking=True)  # ... whose actions are in host memory
+            torch.cuda.current_stream().synchronize()
+            env.step_host(host)
+
+    for _ in range(2):
+        one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    calls = max(1, steps // T)
+    for _ in range(calls):
+        one()
+    wall = (time.perf_counter() - t0) * 1e3
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), wall)
+    if world > 1:
+        t = torch.tensor([ms], device=env.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / (calls * T)
+
+
+def d2h_bytes(host, n, A, T=1, policy_roundtrip=True):
+    total = sum(v.numel() * v.element_size() for k, v in host.items() if v is not None and k != "actions") // T
+    return total + (n * A if policy_roundtrip else 0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    from collectivecrossing_b200 import BatchedCollectiveCrossing
     from collectivecrossing_b200.distributed import ShardedCollectiveCrossing
 
     rank = int(os.environ.get("RANK", "0"))
@@ -384,22 +458,32 @@ def run_ours(args):
         env.step(policy=args.policy)
     if T > 1:
         env.rollout_trajectory(T, policy=args.policy)   # allocates the [T, N, ...] output buffers, warms the fused launch
+    if world > 1:
+        sharded.global_stats_device()                   # warms the NCCL communicator
     torch.cuda.synchronize()
     env.reset_stats()
-    launches0 = env.launch_count
 
+    # the timed region (K steps) is repeated; the median repetition is the value, every repetition is reported
+    reps = max(1, args.reps)
     sampler = ClockSampler(local) if rank == 0 else None
+    rep_ms, stats_t, launches = [], None, 0
     if sampler:
         sampler.mark_begin()
-    ms = time_steps(env, torch, dist, args, args.steps, args.policy, world, T)
+    for _ in range(reps):
+        launches0 = env.launch_count
+        ms_r, stats_t = time_steps(env, torch, dist, args, args.steps, args.policy, world, T, sharded if world > 1 else None)
+        launches = env.launch_count - launches0
+        rep_ms.append(ms_r)
     if sampler:
         sampler.mark_end()
     clocks = sampler.stop() if sampler else None
-    launches = env.launch_count - launches0
+    ms = median(rep_ms)
     env.check_error()
+    kernel_name = env.last_kernel_name
 
-    # episode statistics: the one collective of the job (NCCL all-reduce of 8 scalars per chunk)
-    st = sharded.global_stats()
+    # episode statistics of the job: at world > 1 the tensor the in-loop all-reduce left on the device
+    st = sharded.stats_from_tensor(stats_t) if stats_t is not None else sharded.global_stats()
+    collectives = (args.steps // T + args.steps % T if T > 1 else args.steps) if world > 1 else 0
 
     agent_steps = float(n) * A * args.steps * world
     value = agent_steps / (ms * 1e-3)
@@ -425,64 +509,73 @@ def run_ours(args):
                 traffic = int(table[f"{args.obs_dtype}_{args.policy}_{n}_T20"] * T / 20)   # same kernel, same traffic per step
         except Exception:
             traffic = None
-    kernel_name = ("ccb::cc_step_tpe_kernel<8,%s>" if env.last_kernel == "threads" else "ccb::cc_kernel<8,1,%s,step>") % {"float32": 4, "int8": 1, "none": 0}[args.obs_dtype]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_env_step": total_bytes / (n * args.steps), "steps_per_launch": T,
                 "algorithmic_bytes_per_launch": bT * T * n if T > 1 else b1 * n,
                 "formula": "12A+17+s_obs*A*(6+4A), A=8 (SURVEY.md 8d); in a fused launch of T steps the state term 2(3A+4)+8 is paid once per T steps"}
 
-    # ---- e2e: host buffers through the C ABI (cc_policy_actions -> D2H -> cc_step_host) ----------
+    # ---- e2e (headline): the reference's float32 rows in HOST buffers through the C ABI ----------------------------------
+    launches_before_e2e = env.launch_count
     host = env.make_host_buffers(pinned=True)
-    dev_actions = torch.zeros((n, A), dtype=torch.int8, device=dev)
+    e2e_ms = time_e2e(env, torch, dist, world, args.policy, args.e2e_steps, host)
+    e2e = {"value": float(n) * A * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * A,
+           "d2h_bytes_per_step": d2h_bytes(host, n, A), "steps": args.e2e_steps, "ms_per_step": e2e_ms,
+           "path": "cc_policy_actions -> D2H actions (pinned) -> cc_step_host(H2D actions | fused step kernel | D2H obs/reward/flags, "
+                   "chunks of envs pipelined over three streams); observations are the reference's float32 rows"}
+    launches_e2e = env.launch_count - launches_before_e2e
+    del host
 
-    def e2e_step():
-        env.policy_actions(args.policy, out=dev_actions)
-        host["actions"].copy_(dev_actions, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        env.step_host(host)
+    # ---- the same path with the other delivery formats of the SAME step (labelled, never the headline) ----------------------
+    e2e_modes = {}
+    if not args.no_extras:
+        def mode(tag, obs, expand=0, T_=1, on_device=False, note=""):
+            e = BatchedCollectiveCrossing(cfg, n, dev, seed=2026, global_env_offset=rank * n, obs_dtype=obs or "none", auto_reset=True)
+            e.set_host_expand(expand)
+            e.reset()
+            h = e.make_host_buffers(pinned=True, n_steps=None if T_ == 1 else T_)
+            ms_ = time_e2e(e, torch, dist, world, args.policy, max(args.e2e_steps, 2 * T_), h, T=T_, on_device_policy=on_device)
+            pcie = d2h_bytes(h, n, A, T_, policy_roundtrip=(T_ == 1 and not on_device))
+            if expand:
+                pcie -= h["obs"].numel() * h["obs"].element_size() // T_ - n * A * 4   # the table crosses PCIe, not the rows
+            e2e_modes[tag] = {"agent_steps_per_sec": float(n) * A * world / (ms_ * 1e-3), "ms_per_step": ms_, "d2h_bytes_per_step": pcie,
+                              "vs_float32_rows": e2e_ms / ms_, "note": note}
+            e.close()
+            del e, h
+            torch.cuda.empty_cache()
 
-    for _ in range(3):
-        e2e_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    wall = (time.perf_counter() - t0) * 1e3
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = max(e0.elapsed_time(e1), wall)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    obs_bytes = 0 if host["obs"] is None else host["obs"].numel() * host["obs"].element_size()
-    d2h = n * A + obs_bytes + host["reward"].numel() * 4 + 2 * n * A + n  # policy actions, obs, reward, flags+actions_out, env_flags
-    e2e = {"value": float(n) * A * args.e2e_steps * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * A,
-           "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-           "path": "cc_policy_actions -> D2H actions (pinned) -> cc_step_host(H2D actions, fused step kernel, D2H obs/reward/flags)"}
-    launches_e2e = env.launch_count - launches0 - launches
+        mode("table", "table", note="obs = compact table int8 [N,A,4] (CC_OBS_TABLE); rows on demand through cc_expand_obs_host")
+        if world == 1:
+            mode("int8_rows", "int8", note="obs = the reference's rows as int8")
+            mode("table_policy_on_device", "table", on_device=True, note="cc_step_host with the greedy policy in the kernel: no action round trip")
+            mode("rollout_host_T8_table", "table", T_=8, note="cc_rollout_host: 8 steps per call, chunks stream out while the next chunk runs")
+            mode("float32_rows_rebuilt_on_host", "float32", expand=-1,
+                 note="cc_set_host_expand(-1): the table crosses PCIe, the float32 rows are rebuilt in the caller's buffer by all host threads")
 
     extras = {}
-    if not args.no_extras and world == 1:
-        del host
-        extras = secondary(args, torch, dist, cfg)
+    if not args.no_extras:
+        if world == 1:
+            extras = secondary(args, torch, dist, cfg)
+        else:
+            extras = config5_sharded(args, torch, dist, cfg, world, rank, dev)
 
     if all_cpus:
         os.sched_setaffinity(0, all_cpus)
     if rank == 0:
-        cpu = cpu_c_oracle(args, args.cpu_seconds) if world == 1 else None
+        cpu = None
+        if world == 1:
+            cpu = cpu_python_loop(args, args.cpu_seconds)
+            c_orc = cpu_c_oracle(args, min(4.0, args.cpu_seconds))
+            cpu["c_oracle_openmp"] = {"value": c_orc["value"], "cores": c_orc["cores"], "sample": c_orc["sample"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 lattice state, float64->float32 rewards", "data": "synthetic",
             "config": config_dict(args, n * world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "gpu_launches_e2e": launches_e2e, "roofline": roofline, "cpu_baseline": cpu,
-            "episode_stats": st, "extras": extras,
+            "repetitions": {"count": reps, "ms_per_region": rep_ms, "value": "median", "spread": (max(rep_ms) - min(rep_ms)) / ms},
+            "collectives_in_timed_region": {"count": collectives, "what": "NCCL all-reduce (SUM) of the 8 episode statistics, one per launch, enqueued behind the kernel"},
+            "episode_stats": st, "e2e_modes": e2e_modes, "host_copy_GBps": host_copy_bandwidth(torch) if world == 1 else None, "extras": extras,
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -493,96 +586,107 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def config5_sharded(args, torch, dist, cfg, world, rank, dev):
+    """BASELINE config 5 as stated: 16,777,216 README envs sharded over the job's GPUs, waiting policy in the kernel, auto-reset,
+    float32 rows, fused launches of 8 env-steps with ONE NCCL all-reduce of the episode statistics per launch inside the timed
+    region (median of 3 regions of 5 launches)."""
+    from collectivecrossing_b200.distributed import ShardedCollectiveCrossing
+
+    total, T, launches = 1 << 24, 8, 5
+    sh = ShardedCollectiveCrossing(cfg, total, seed=5, device=dev, obs_dtype="float32", auto_reset=True)
+    env = sh.env
+    env.reset()
+    for _ in range(30):
+        env.step(policy="waiting")
+    env.rollout_trajectory(T, policy="waiting")
+    sh.global_stats_device()
+    env.reset_stats()
+    regions, stats_t = [], None
+    for _ in range(3):
+        ms, stats_t = time_steps(env, torch, dist, args, T * launches, "waiting", world, T, sh)
+        regions.append(ms)
+    ms = median(regions)
+    st = sh.stats_from_tensor(stats_t)
+    env.check_error()
+    out = {"cfg5_16M_envs_waiting_sharded": {
+        "agent_steps_per_sec": float(total) * 8 * T * launches / (ms * 1e-3), "ms_per_step": ms / (T * launches), "envs_total": total, "envs_per_gpu": sh.count,
+        "n_gpus": world, "steps_per_launch": T, "ms_per_region": regions, "collectives_per_region": launches, "kernel": env.last_kernel_name,
+        "episodes": st["episodes"], "episode_len_mean": st["episode_len_mean"], "terminated_fraction": st["terminated_fraction"],
+        "algorithmic_GBps_per_gpu": (1329 - 64 * (1 - 1 / T)) * sh.count * T * launches / (ms * 1e-3) / 1e9}}
+    env.close()
+    return out
+
+
 def secondary(args, torch, dist, cfg):
-    """Secondary single-GPU measurements (reported under "extras", never as `value`): the other obs
-    dtypes / policies of the headline config, the lane-group mapping, and the shapes of BASELINE
-    configs 3, 4 and 5 on one GPU."""
+    """Secondary single-GPU measurements (reported under "extras", never as `value`): the other output modes / policies of the
+    headline config (single-step launches, median of 3 regions), the lane-group mapping, small batches, and the shapes of BASELINE
+    configs 3, 4 and 5 on one GPU.  `frac` = algorithmic bytes / time / the measured HBM peak."""
     from cases import large_config, readme_config
 
     from collectivecrossing_b200 import BatchedCollectiveCrossing
 
     out = {}
     dev = torch.device("cuda", torch.cuda.current_device())
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    peak = float(json.loads(peaks_path.read_text())["hbm_gbs"]) if peaks_path.exists() else 6650.0
     M = 1 << 20
+    binary = readme_config("binary", "individual", 100, goal_reward=1.0, no_goal_reward=0.0)
+    constneg = readme_config("constant_negative", "individual", 100, step_penalty=-1.0)
     runs = (
-        # tag, config, envs, obs dtype, policy, kernel, timed steps
-        ("1M_envs_fp32_greedy_single_step_launches", cfg, M, "float32", "greedy", "auto", 50),
-        ("cfg2_65536_envs_fp32_greedy", cfg, 65536, "float32", "greedy", "auto", 50),
-        ("1M_envs_int8_greedy", cfg, M, "int8", "greedy", "auto", 50),
-        ("1M_envs_noobs_greedy", cfg, M, "none", "greedy", "auto", 50),
-        ("1M_envs_fp32_waiting", cfg, M, "float32", "waiting", "auto", 50),
-        ("1M_envs_fp32_random", cfg, M, "float32", "random", "auto", 50),
-        ("1M_envs_fp32_greedy_lane_group_kernel", cfg, M, "float32", "greedy", "lanes", 50),
-        ("cfg4_binary_individual_4M_envs_fp32_random", readme_config("binary", "individual", 100, goal_reward=1.0, no_goal_reward=0.0), 4 * M, "float32", "random", "auto", 10),
-        ("cfg4_constant_negative_individual_4M_envs_fp32_random", readme_config("constant_negative", "individual", 100, step_penalty=-1.0), 4 * M, "float32", "random", "auto", 10),
-        ("cfg5_shard_2M_envs_fp32_waiting", cfg, 2 * M, "float32", "waiting", "auto", 20),
-        ("cfg3_64x32_64agents_simple_distance_all_1M_envs_int8_random", large_config(512), M, "int8", "random", "auto", 5),
-        ("cfg3_64x32_64agents_simple_distance_all_1M_envs_fp32_random", large_config(512), M, "float32", "random", "auto", 3),
+        # tag, config, envs, obs dtype, policy, kernel, timed steps per region, steps per launch
+        ("1M_envs_fp32_greedy_single_step_launches", cfg, M, "float32", "greedy", "auto", 50, 1),
+        ("1M_envs_int8_greedy", cfg, M, "int8", "greedy", "auto", 50, 1),
+        ("1M_envs_int8_greedy_fused20", cfg, M, "int8", "greedy", "auto", 40, 20),
+        ("1M_envs_table_greedy", cfg, M, "table", "greedy", "auto", 50, 1),
+        ("1M_envs_noobs_greedy", cfg, M, "none", "greedy", "auto", 50, 1),
+        ("1M_envs_noobs_greedy_fused20", cfg, M, "none", "greedy", "auto", 40, 20),
+        ("1M_envs_int8_waiting", cfg, M, "int8", "waiting", "auto", 50, 1),
+        ("1M_envs_fp32_waiting", cfg, M, "float32", "waiting", "auto", 50, 1),
+        ("1M_envs_fp32_random", cfg, M, "float32", "random", "auto", 50, 1),
+        ("1M_envs_fp32_greedy_lane_group_kernel", cfg, M, "float32", "greedy", "lanes", 50, 1),
+        ("cfg2_65536_envs_fp32_greedy", cfg, 65536, "float32", "greedy", "auto", 100, 1),
+        ("cfg2_65536_envs_fp32_greedy_fused20", cfg, 65536, "float32", "greedy", "auto", 200, 20),
+        ("cfg4_binary_individual_4M_envs_fp32_random", binary, 4 * M, "float32", "random", "auto", 10, 1),
+        ("cfg4_constant_negative_individual_4M_envs_fp32_random", constneg, 4 * M, "float32", "random", "auto", 10, 1),
+        ("cfg5_shard_2M_envs_fp32_waiting", cfg, 2 * M, "float32", "waiting", "auto", 20, 1),
+        ("cfg3_64x32_64agents_simple_distance_all_1M_envs_int8_random", large_config(512), M, "int8", "random", "auto", 5, 1),
+        ("cfg3_64x32_64agents_simple_distance_all_1M_envs_fp32_random", large_config(512), M, "float32", "random", "auto", 3, 1),
     )
-    for tag, c, n, obs, pol, kern, steps in runs:
+    for tag, c, n, obs, pol, kern, steps, T in runs:
         env = BatchedCollectiveCrossing(c, n, dev, seed=1, obs_dtype=obs, auto_reset=True, kernel=kern)
         env.reset()
         for _ in range(5):
             env.step(policy=pol)
-        ms = time_steps(env, torch, dist, args, steps, pol, 1)
+        if T > 1:
+            env.rollout_trajectory(T, policy=pol)
+        regions = [time_steps(env, torch, dist, args, steps, pol, 1, T)[0] for _ in range(3)]
+        ms = median(regions)
         env.check_error()
-        b = env.algorithmic_bytes_per_env_step() * n
         a = env.num_agents
-        out[tag] = {"agent_steps_per_sec": n * a * steps / (ms * 1e-3), "ms_per_step": ms / steps, "algorithmic_GBps": b / (ms / steps * 1e-3) / 1e9,
-                    "kernel": env.last_kernel, "agents_per_env": a, "envs": n}
+        b1 = env.algorithmic_bytes_per_env_step()
+        bT = b1 - (2 * (3 * a + 4) + 8) * (1.0 - 1.0 / T)
+        gbs = bT * n / (ms / steps * 1e-3) / 1e9
+        out[tag] = {"agent_steps_per_sec": n * a * steps / (ms * 1e-3), "ms_per_step": ms / steps, "algorithmic_GBps": gbs, "frac": gbs / peak,
+                    "algorithmic_bytes_per_env_step": bT, "kernel": env.last_kernel_name, "agents_per_env": a, "envs": n, "steps_per_launch": T,
+                    "ms_per_region": regions}
         env.close()
         del env
         torch.cuda.empty_cache()
-    # the host-buffer path with the compact int8 observation rows (4x less PCIe traffic than the reference's float32 rows;
-    # a consumer that needs float32 widens them on its side) — reported beside the float32 `e2e`, never instead of it
-    env = BatchedCollectiveCrossing(cfg, M, dev, seed=1, obs_dtype="int8", auto_reset=True)
-    env.reset()
-    host = env.make_host_buffers(pinned=True)
-    dev_actions = torch.zeros((M, env.num_agents), dtype=torch.int8, device=dev)
 
-    def e2e_step():
-        env.policy_actions("greedy", out=dev_actions)
-        host["actions"].copy_(dev_actions, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        env.step_host(host)
-
-    for _ in range(3):
-        e2e_step()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(12):
-        e2e_step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    out["e2e_host_buffers_int8_obs_1M_envs"] = {"agent_steps_per_sec": M * env.num_agents * 12 / dt, "ms_per_step": dt / 12 * 1e3,
-                                                "d2h_bytes_per_step": M * env.num_agents * (env.obs_len + 4 + 3) + M, "kernel": env.last_kernel,
-                                                "algorithmic_GBps": 0.0, "agents_per_env": env.num_agents, "envs": M}
-    env.close()
-    del env, host
-    torch.cuda.empty_cache()
-
-    # fused multi-step launches (cc_rollout_fused): T env-steps per env per launch, the state stays in registers;
-    # every step's observations, rewards and flags are still written ([T, N, ...] buffers).  Algorithmic bytes per
-    # env-step: the state term 2(3A+4)+8 of SURVEY.md 8d is paid once per T steps.
-    for T, n_envs in ((4, M), (16, M), (20, 65536)):
+    # fused multi-step launches of the headline kernel at other lengths (the state term 2(3A+4)+8 is paid once per T steps)
+    for T, n_envs in ((4, M), (16, M)):
         env = BatchedCollectiveCrossing(cfg, n_envs, dev, seed=1, obs_dtype="float32", auto_reset=True)
         env.reset()
         env.rollout_trajectory(T, policy="greedy")
-        launches = 12
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(launches):
-            env.rollout_trajectory(T, policy="greedy")
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / (launches * T)
+        regions = [time_steps(env, torch, dist, args, 12 * T, "greedy", 1, T)[0] / (12 * T) for _ in range(3)]
+        ms = median(regions)
         env.check_error()
         a = env.num_agents
         bytes_step = a + (2 * (3 * a + 4) + 8) / T + 5 * a + 1 + 4 * a * (6 + 4 * a)
-        out[f"fused_rollout_T{T}_{'1M' if n_envs == M else n_envs}_envs_fp32_greedy"] = {
+        out[f"fused_rollout_T{T}_1M_envs_fp32_greedy"] = {
             "agent_steps_per_sec": n_envs * a / (ms * 1e-3), "ms_per_step": ms, "algorithmic_GBps": bytes_step * n_envs / (ms * 1e-3) / 1e9,
-            "algorithmic_bytes_per_env_step": bytes_step, "kernel": env.last_kernel, "agents_per_env": a, "envs": n_envs, "steps_per_launch": T}
+            "frac": bytes_step * n_envs / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_env_step": bytes_step, "kernel": env.last_kernel_name,
+            "agents_per_env": a, "envs": n_envs, "steps_per_launch": T}
         env.close()
         del env
         torch.cuda.empty_cache()

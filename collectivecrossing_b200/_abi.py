@@ -91,6 +91,7 @@ EXPORTS = {
     "cc_observe": (C.c_int, [_P, _P, _I32, _P]),
     "cc_stats_read": (C.c_int, [_P, C.POINTER(CCStats), _P]),
     "cc_stats_reset": (C.c_int, [_P, _P]),
+    "cc_stats_copy": (C.c_int, [_P, _P, _P]),
     "cc_check_error": (C.c_int, [_P, _P]),
     "cc_num_envs": (_I64, [_P]),
     "cc_num_agents": (_I32, [_P]),

@@ -22,7 +22,8 @@ class NativeError(RuntimeError):
 
 def build(force: bool = False) -> Path:
     """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
-    cmd = ["make", "-s", "-j", str(min(8, os.cpu_count() or 1)), "-C", str(CSRC)] + (["-B"] if force else [])
+    # `all`: the library and its checked twin (device-side bounds asserts, tests/test_gpu_checked_build.py)
+    cmd = ["make", "-s", "-j", str(min(8, os.cpu_count() or 1)), "-C", str(CSRC), "all"] + (["-B"] if force else [])
     subprocess.run(cmd, check=True)
     return LIB_PATH
 

@@ -418,6 +418,19 @@ class BatchedCollectiveCrossing:
         _native.check(self._lib.cc_stats_read(self._h, C.byref(st), self._stream()))
         return st.as_dict()
 
+    def stats_device(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """The statistics block as a float64 [8] DEVICE tensor (``distributed.STAT_KEYS`` order), with no host round trip:
+        what the multi-GPU reduction all-reduces behind the step kernels."""
+        raw = getattr(self, "_stats_raw", None)
+        if raw is None:
+            raw = self._stats_raw = torch.zeros(8, dtype=torch.int64, device=self.device)
+        _native.check(self._lib.cc_stats_copy(self._h, raw.data_ptr(), self._stream()))
+        vals = torch.cat([raw[:6].to(torch.float64), raw[6:].view(torch.float64)])
+        if out is not None:
+            out.copy_(vals)
+            return out
+        return vals
+
     def reset_stats(self) -> None:
         _native.check(self._lib.cc_stats_reset(self._h, self._stream()))
 

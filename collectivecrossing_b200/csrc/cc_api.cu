@@ -633,6 +633,12 @@ int cc_stats_read(cc_handle *h, cc_stats *out, void *stream) {
     CC_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     return CC_OK;
 }
+int cc_stats_copy(cc_handle *h, void *out_device, void *stream) {
+    if (!h || !out_device) return cc_fail(CC_ERR_INVALID_ARG, "null handle or out");
+    DeviceGuard guard(h->device);
+    CC_CUDA(cudaMemcpyAsync(out_device, h->stats, sizeof(cc_stats), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return CC_OK;
+}
 int cc_stats_reset(cc_handle *h, void *stream) {
     if (!h) return cc_fail(CC_ERR_INVALID_ARG, "null handle");
     DeviceGuard guard(h->device);

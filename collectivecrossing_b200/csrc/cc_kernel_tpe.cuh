@@ -209,6 +209,7 @@ __device__ __forceinline__ void tpe_emit_group_tma(const unsigned *lut, unsigned
             asm volatile("{\n\t.reg .pred pl;\n\tsetp.ne.u32 pl, %1, 0xFFFFFFFF;\n\t@pl ld.shared.b64 %0, [%2];\n\t}"
                          : "+l"(val[j]) : "r"(src[j]), "r"(src[j] + t_imm));
 #else
+            CCB_CHECK(src[j] + t_imm >= sbase && src[j] + t_imm + 8u <= sbase + (unsigned)L::kTplBytesPerWarp);
             asm volatile("ld.shared.b64 %0, [%1];" : "=l"(val[j]) : "r"(src[j] + t_imm));
 #endif
             if (j * 32 + 32 <= L::PPE || lane + j * 32 < L::PPE)
@@ -216,6 +217,7 @@ __device__ __forceinline__ void tpe_emit_group_tma(const unsigned *lut, unsigned
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy read
         __syncwarp();
+        CCB_CHECK(buf + (unsigned)L::kImgBytes <= (unsigned)(L::kImgRing * L::kImgBytes) && (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
         if (lane == 0) {
             // (evict_first: the rows are written once and not read by this kernel; they must not push the state out of L2)
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
@@ -299,8 +301,9 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
     // address arithmetic per access was a fifth of the policy's instructions)
     const unsigned bm = (unsigned)__cvta_generic_to_shared(bm_ptr);
     constexpr unsigned kBmWord = 4u * kBmStride;   // bytes between consecutive words of one thread
-    auto bm_load = [&](unsigned word) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(bm + word * kBmWord)); return v; };
-    auto bm_store = [&](unsigned word, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(bm + word * kBmWord), "r"(v) : "memory"); };
+    // (checked build: a word of the private bitmap lies inside the region it aliases — the warp's image ring — or its own)
+    auto bm_load = [&](unsigned word) { CCB_CHECK((int)word < p.tpe_bm_words && (!L::kTma || (word + 1) * kBmWord <= (unsigned)(L::kImgRing * L::kImgBytes))); unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(bm + word * kBmWord)); return v; };
+    auto bm_store = [&](unsigned word, unsigned v) { CCB_CHECK((int)word < p.tpe_bm_words && (!L::kTma || (word + 1) * kBmWord <= (unsigned)(L::kImgRing * L::kImgBytes))); asm volatile("st.shared.u32 [%0], %1;" ::"r"(bm + word * kBmWord), "r"(v) : "memory"); };
 
     // ---- once per CTA: tables (same contents as cc_kernels.cuh) -------------------------------------
     for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
@@ -427,6 +430,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             // (clamped to the lattice: set_state promises in-lattice positions, the clamp only keeps the
             // table and bitmap reads of garbage in bounds — all four neighbours lie in the padded lattice)
             const int cx = min((int)(pos[k] >> 8), p.W) + 1, cy = min((int)(pos[k] & 0xffu), p.H) + 1;
+            CCB_CHECK(cx >= 1 && cx <= p.W + 1 && cy >= 1 && cy <= p.H + 1);
             const unsigned xv = xt[cx], yv = yt[(k < p.B ? 0 : kMaxPad) + cy];
             cell[k] = cy * PW + cx;
             geo_u[k] = yv + xv;
@@ -517,6 +521,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
             }
 #pragma unroll
             for (int k = 0; k < A; ++k) {
+                CCB_CHECK((((geo_u[k] & 0xffu) << 4) | vmask[k]) < kPolicyRows * 16);
                 const unsigned a = act_tab[((geo_u[k] & 0xffu) << 4) | vmask[k]];
                 const bool asks = (fl[k] & 7u) == CC_F_ACTIVE;                         // active, not done
                 const bool waits = exiting_pending && k < p.B && !(geo_f[k] & 1u);    // waiting_policy.py:74-108
@@ -569,6 +574,7 @@ __global__ void __launch_bounds__(kTpeThreads, CCB_TPE_MIN_BLOCKS) cc_step_tpe_k
         for (int k = 0; k < A; ++k) {
             // one path for the four reward functions, see cc_kernels.cuh (rewards.py:65-66,78-99,127,152-159,179-182)
             const unsigned f = geo_f[k];
+            CCB_CHECK((int)((geo_u[k] >> 8) & 0x1ffu) < kRtabSize);
             float r = rtab[(int)((geo_u[k] >> 8) & 0x1ffu)];
             if (k >= p.B && p.reward_kind == CC_REWARD_DEFAULT) r = 0.f - r;   // rewards.py:95-99: the exiting term is positive (sic)
             const bool boarding = k < p.B;

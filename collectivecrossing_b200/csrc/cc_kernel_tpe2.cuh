@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
     const unsigned typew0 = kM0 & ~boardw[0], typew1 = kM1 & ~boardw[1];   // observations.py:86: 0 boarding, 1 exiting
 
     auto lookup = [&](unsigned c, int k) {
+        CCB_CHECK(c < (unsigned)kT2MaxCells);
         uint2 e;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(tbase[k] + c * 16u));
         return e;
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
 #pragma unroll
             for (int k = 0; k < A; ++k) {
                 arow[k] = bm + 128u + ((e[k].x >> 9) & 0x780u);                       // row y + 1
+                CCB_CHECK(arow[k] >= bm + 128u && arow[k] + 128u < bm + 128u * (unsigned)PH && ((e[k].x >> 8) & 31u) + 2u <= 31u);
                 if ((fl[k >> 2] >> (8 * (k & 3))) & 1u)                               // column x + 1
                     asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(arow[k]), "r"(2u << ((e[k].x >> 8) & 31u)) : "memory");
             }
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                 const unsigned occ = (here & 5u) | (above & 2u) | ((below & 2u) << 2);
                 const unsigned vmask = (e[k].x >> 24) & 15u & ~occ;
                 unsigned a;
+                CCB_CHECK((((e[k].x & 31u) << 4) | vmask) < (unsigned)(kPolicyRows * 16));
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(a) : "r"(act_s + (((e[k].x & 31u) << 4) | vmask)));
                 const unsigned m = t2_fill(k < 4 ? go7[0] : go7[1], k & 3);
                 act[k] = ((a ^ (unsigned)CC_ACT_WAIT) & m) ^ (unsigned)CC_ACT_WAIT;
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
             // one agent's turn: the target is committed unless some cmp value equals it — a chain of setp.eq.or on ONE predicate
             // (the compiler's own rendering of the same test is a compare + select per pair)
             auto turn = [&](const int k, const int d) {
+                CCB_CHECK(act[k] <= 4u && (am[k] == 0u || c[k] + (unsigned)d < (unsigned)kT2MaxCells));
                 const unsigned target = (c[k] + (unsigned)d) | ~am[k];
                 auto cm = [&](int j) { return cmp[j < A ? j : 0]; };
                 asm("{\n\t.reg .pred q;\n\t"
@@ -447,6 +451,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                     if (i < B) { cx = bounded(r.v0, p.W); cy = bounded(r.v1, p.D); }                                   // :103-117
                     else { cx = p.TL + bounded(r.v0, p.TR + 1 - p.TL); cy = p.D + bounded(r.v1, p.H - p.D); }            // :132-140
                     cand = (unsigned)((cy + 1) * PW + cx + 1);
+                    CCB_CHECK(cand < (unsigned)(PW * PH));
                     const unsigned ge = tb.tab[(cand & 255u) * 2].x;
                     ok = (ge & kT2Valid) && !(i < B && (ge & kT2SpawnExcluded));
 #pragma unroll
@@ -507,6 +512,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                     for (int j = 0; j < 8; ++j) w[11 + j] = j == b ? 0xffffffffu : T[j];
                 }
                 const unsigned dst_s = img_s + (unsigned)lane * (unsigned)L::kEnvBytes;
+                CCB_CHECK(dst_s + 19u * 16u <= img_s + (unsigned)L::kBytesPerWarp && envs_here * L::kEnvBytes <= L::kImageBytes && (envs_here * L::kEnvBytes) % 16 == 0);
 #pragma unroll
                 for (int v = 0; v < 19; ++v)
                     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst_s + 16u * v), "r"(wv[4 * v]), "r"(wv[4 * v + 1]), "r"(wv[4 * v + 2]), "r"(wv[4 * v + 3]) : "memory");

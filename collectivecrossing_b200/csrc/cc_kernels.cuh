@@ -22,6 +22,16 @@
 #define CCB_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must allow (A/B in DESIGN.md §6)
 #endif
 
+// Checked build (make CHECKS=1 -> libccb200_checked.so; tests/test_gpu_checked_build.py runs parity cases through it):
+// device-side asserts on every data-dependent shared-memory index and on the bulk-copy sizes.  compute-sanitizer is closed
+// on this pool (profiles/r2_compute_sanitizer_closed_on_this_pool.txt), so these are the bounds checks of the hot path.
+#ifdef CCB_CHECKS
+#include <cassert>
+#define CCB_CHECK(cond) assert(cond)
+#else
+#define CCB_CHECK(cond) ((void)0)
+#endif
+
 namespace ccb {
 
 constexpr int kWarpsPerCta = 8;
@@ -490,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
         unsigned geo_u[APL], geo_f[APL];
         auto lookup = [&](int k) {
             const int cx = min((int)(pos[k] >> 8), p.W + 1) + 1, cy = min((int)(pos[k] & 0xffu), p.H + 1) + 1;
+            CCB_CHECK(cx >= 0 && cx < kMaxPad && cy >= 0 && ytoff[k] + cy < 2 * kMaxPad);
             const unsigned xv = xt[cx], yv = yt[ytoff[k] + cy];
             cell[k] = cy * PW + cx;
             geo_u[k] = yv + xv;
@@ -514,6 +525,7 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
 #pragma unroll
                 for (int k = 0; k < APL; ++k) {
                     lookup(k);
+                    CCB_CHECK(cell[k] >= PW && cell[k] + PW < p.walk_words * 32);   // the four neighbours lie inside the padded lattice
                     if (fl[k] & CC_F_ACTIVE) atomicOr(&blocked[cell[k] >> 5], 1u << (cell[k] & 31));
                     // waiting_policy.py:118-131: some exiting agent that is not done has not arrived
                     pending |= avalid[k] && aidx[k] >= p.B && (fl[k] & 6u) == 0u && env_ok && !(geo_f[k] & 8u);
@@ -526,6 +538,7 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
                     const int c = cell[k];
                     auto is_free = [&](int idx) { return ((blocked[idx >> 5] >> (idx & 31)) & 1u) ^ 1u; };
                     const unsigned vmask = is_free(c + 1) | (is_free(c + PW) << 1) | (is_free(c - 1) << 2) | (is_free(c - PW) << 3);
+                    CCB_CHECK((((geo_u[k] & 0xffu) << 4) | vmask) < kPolicyRows * 16);
                     const int a = act_tab[((geo_u[k] & 0xffu) << 4) | vmask];
                     const bool asks = (fl[k] & 7u) == CC_F_ACTIVE;                         // active, not done
                     const bool waits = exiting_pending && aidx[k] < p.B && !(geo_f[k] & 1u);  // waiting_policy.py:74-108
@@ -663,6 +676,7 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
                 // (a constant for binary / constant_negative), and the DefaultReward categories
                 // (rewards.py:78-99) override it where their mask bits are set (masks are 0 for the others).
                 const unsigned f = geo_f[k];
+                CCB_CHECK(rtoff[k] + (int)((geo_u[k] >> 8) & 0x1ffu) < 2 * kRtabSize);
                 float r = rtab[rtoff[k] + (int)((geo_u[k] >> 8) & 0x1ffu)];       // :82-85 / :95-99 (positive, sic) / :127
                 const bool boarding = aidx[k] < p.B;
                 const float special = boarding ? ((f & 2u) ? p.rpf[1] : p.rpf[2]) : p.rpf[2];  // door / tram area | exiting outside (sic)
@@ -912,13 +926,17 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
                     const int n_plain = vcount[0], n_special = vcount[1];
                     for (int idx = T.lane; idx < n_plain; idx += 32) {
                         const unsigned e = vplain[idx];
+                        CCB_CHECK((int)(e & 0xffffu) < p.nvec_env && (int)(e >> 16) + 16 <= 8 * p.shift_tst && ((e >> 16) & 15u) == 0u);
                         __stcs(outv + (e & 0xffffu), *reinterpret_cast<const uint4 *>(shifted + (e >> 16)));
                     }
                     for (int idx = T.lane; idx < n_special; idx += 32) {
                         const int v = vspecial[idx];
                         union { uint4 u; P2 e[PPV]; } pk;
 #pragma unroll
-                        for (int c = 0; c < PPV; ++c) pk.e[c] = stage[lut[v * PPV + c]];
+                        for (int c = 0; c < PPV; ++c) {
+                            CCB_CHECK(v * PPV + c < p.lut_entries && lut[v * PPV + c] < p.stage_pairs);
+                            pk.e[c] = stage[lut[v * PPV + c]];
+                        }
                         __stcs(outv + v, pk.u);
                     }
                 }

@@ -99,6 +99,21 @@ class ShardedCollectiveCrossing:
         st = self.env.stats
         return st() if callable(st) else st
 
+    def global_stats_device(self) -> torch.Tensor:
+        """Episode statistics summed over the ranks as a float64 [8] DEVICE tensor (``STAT_KEYS`` order): the per-rank block is
+        copied on the device and all-reduced (NCCL) behind the step kernels — nothing waits on the host, so a rollout loop can
+        call this once per chunk.  ``stats_from_tensor`` turns the result into the dict ``global_stats`` returns."""
+        t = self.env.stats_device()
+        if self.world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    @staticmethod
+    def stats_from_tensor(t: torch.Tensor) -> dict:
+        out = {k: (int(round(v)) if k not in ("episode_return_sum", "reward_sum") else v) for k, v in zip(STAT_KEYS, t.tolist())}
+        out.update(derived_stats(out))
+        return out
+
     def global_stats(self) -> dict:
         dev = self.device if (self.device is not None and dist.is_initialized() and dist.get_backend() == "nccl") else "cpu"
         out = reduce_stats(self.local_stats(), dev)

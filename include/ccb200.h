@@ -280,6 +280,9 @@ int cc_observe(cc_handle *h, void *obs, int32_t obs_dtype, void *stream);
 /* --- bookkeeping ---------------------------------------------------------------------- */
 int cc_stats_read(cc_handle *h, cc_stats *out, void *stream); /* synchronises `stream` */
 int cc_stats_reset(cc_handle *h, void *stream);
+/* The same block without a host round trip: 64 bytes (the cc_stats layout) copied to a DEVICE buffer on `stream`, so that the
+ * multi-GPU reduction (one NCCL all-reduce per rollout chunk) can be enqueued behind the step kernels with no synchronisation. */
+int cc_stats_copy(cc_handle *h, void *out_device, void *stream);
 /* sticky device error raised by kernels since the last call (CC_OK if none); clears it. */
 int cc_check_error(cc_handle *h, void *stream);
 int64_t cc_num_envs(const cc_handle *h);
