@@ -3,6 +3,7 @@
 // instantiated in cc_launch_lanes.cu / cc_launch_tpe.cu; the host-side row expansion is cc_expand.cpp.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -78,7 +79,11 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     p.R = 3 + 2 * A;
     p.pairs_per_env = A * p.R;
     const bool rows = is_rows(obs_dtype);
-    p.lut_entries = rows ? h->epw * p.pairs_per_env : 0;
+    // int8 rows of big crews (one env per warp) whose env block is whole 16-byte vectors: shifted template copies, vector
+    // lists, a LUT for the special vectors only and a ring of chunk images that leave through bulk copies (cc_kernels.cuh)
+    const int env_bytes = A * (6 + 4 * A);
+    const bool shifted = obs_dtype == CC_OBS_INT8 && h->lpe == 32 && h->epw == 1 && env_bytes % 16 == 0 && env_bytes / 16 < 65536;
+    p.lut_entries = (rows && !shifted) ? h->epw * p.pairs_per_env : 0;
     p.stage_pairs = rows ? round_up(h->epw * (2 * A + 4), 8) : 0;  // one row template per env
     p.walk_words = ((c.width + 3) * (c.height + 3) + 31) / 32;
     const int pair_bytes = obs_dtype == CC_OBS_FP32 ? 8 : 2;
@@ -89,15 +94,29 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     off += needs_bitmap ? round_up(ccb::kWarpsPerCta * h->epw * p.walk_words * 4, 16) : 0;
     p.off_desc = off;
     off += (rows && h->lpe <= 16) ? ccb::kDescWords * 4 * ccb::kThreads : 0;
-    // int8 rows of big crews (one env per warp): shifted template copies + vector lists (cc_kernels.cuh)
-    const int env_bytes = A * (6 + 4 * A);
-    if (obs_dtype == CC_OBS_INT8 && h->lpe == 32 && h->epw == 1 && env_bytes % 16 == 0 && env_bytes / 16 < 65536) {
+    if (shifted) {
         p.nvec_env = env_bytes / 16;
         p.shift_tst = round_up(14 + (2 * A + 4) * 2 + 16, 16);
         p.off_shift = off;
         off += ccb::kWarpsPerCta * 8 * p.shift_tst;
+        // a row is 6 + 4A = 2 x odd bytes: 8 rows are the smallest run of rows that is a whole number of 16-byte vectors
+        p.img_vecs = (6 + 4 * A) / 2;
+        p.n_chunks = A / 8;                       // env_bytes % 16 == 0 <=> A % 8 == 0
+        p.max_special = 4 * A + 8;                // per row at most: a straddling vector, a head vector, two that touch the own block
         p.off_vlist = off;
-        off += round_up(p.nvec_env * 6 + 16, 16);
+        off += round_up(p.nvec_env * 6 + 16 + 2 * (p.n_chunks + 1) * 4 + p.max_special * 16, 16);
+        p.off_img = off;
+        off += ccb::kWarpsPerCta * ccb::kLaneImgRing * p.img_vecs * 16;
+    }
+    // one env per warp (crews above 16): byte maps of the padded lattice for the parallel resolution of the ordered moves
+    // (cc_kernels.cuh); lattices whose maps would not fit keep the sequential turns
+    const int cells = round_up((c.width + 3) * (c.height + 3), 16);
+    static const bool cellmaps = [] { const char *v = getenv("CCB200_CELLMAP"); return !(v && v[0] == '0'); }();   // (A/B switch)
+    if (cellmaps && h->lpe == 32 && h->epw == 1 && cells <= 3072) {
+        off = round_up(off, 16);
+        p.off_cellmap = off;
+        p.cellmap_cells = cells;
+        off += ccb::kWarpsPerCta * (2 * cells + 128);
     }
     p.smem_total = off;
     p.n_groups = (count + h->epw - 1) / h->epw;

@@ -18,6 +18,15 @@
 #ifndef CCB_MIN_BLOCKS_APL2
 #define CCB_MIN_BLOCKS_APL2 1   // crews of 33-64 agents (two agents per lane): 108 registers, 2 CTAs per SM (3 CTAs at 76 registers measured slower: 1.63 vs 1.49 ms int8, 3.04 vs 2.77 ms float32 per 262 k envs)
 #endif
+#ifndef CCB_LANES_PREFETCH
+#define CCB_LANES_PREFETCH 1   // one env per warp: request the next env's record before stepping the current one
+#endif
+#ifndef CCB_LANES_PARMOVES
+#define CCB_LANES_PARMOVES 1   // one env per warp: resolve the ordered moves in parallel (shared-memory cell maps)
+#endif
+#ifndef CCB_LANES_UNROLL
+#define CCB_LANES_UNROLL 4     // plain-vector loop of the int8 rows of big crews
+#endif
 #ifndef CCB_MIN_BLOCKS
 #define CCB_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must allow (A/B in DESIGN.md §6)
 #endif
@@ -34,6 +43,8 @@
 
 namespace ccb {
 
+constexpr int kPlainUnroll = CCB_LANES_UNROLL;
+constexpr int kLaneImgRing = 2;   // chunk images per warp (int8 rows of big crews)
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -88,11 +99,18 @@ struct KParams {
     // aligned 16-byte shared-memory load (shift_tst = 0: not used)
     int shift_tst;                // bytes of one shifted copy (multiple of 16)
     int off_shift;                // [warp][8][shift_tst]
-    int off_vlist;                // unsigned plain[nvec_env] then unsigned short special[nvec_env], then 2 counters
+    int off_vlist;                // unsigned plain[nvec_env], unsigned short special[nvec_env], counts[2], starts[2][n_chunks+1], special LUT
+    int img_vecs, n_chunks;       // the env block leaves the SM in n_chunks bulk copies of img_vecs vectors (8 rows: a multiple of 16 bytes)
+    int off_img;                  // [warp][kLaneImgRing][img_vecs * 16] image ring
+    int max_special;              // rows of the special-vector LUT
     int nvec_env;                 // 16-byte vectors of an env's observation block
     long long obs_env_offset;     // lane-group kernel: the observation rows of env n go to row block n + obs_env_offset of p.obs
     int n_steps;                  // env-steps per env in this launch (1 for cc_step)
     const void *t2_tables;        // small-lattice kernel: its tables, built once per handle (cc_kernel_tpe2.cuh: T2Tables)
+    // lane-group kernel, one env per warp (crews above 16): per-warp byte maps of the padded lattice for the parallel
+    // resolution of the ordered moves — [own: which ACTIVE agent stands on the cell][win: first contender for the cell]
+    // [128 status bytes] (cellmap_cells = bytes of one map, a multiple of 16; 0 = sequential turns only)
+    int off_cellmap, cellmap_cells;
     long long slice_agents;       // elements of one time slice of a per-agent array: n_envs * A
     long long slice_envs;         // ... of a per-env array: n_envs
     long long slice_obs_bytes;    // ... of the observation tensor, in bytes
@@ -353,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
                 desc_sm[q * kThreads] = make_uint4(d[0], d[1], d[2], d[3]);
             }
         } else {
-            for (int P = threadIdx.x; P < p.lut_entries; P += blockDim.x) lut[P] = (uint16_t)gather_index(p, P);
+            for (int P = threadIdx.x; P < p.lut_entries; P += blockDim.x) lut[P] = (uint16_t)gather_index(p, P);   // (no entries with shifted rows)
         }
         for (int e = T.lane; e < EPW; e += 32) {   // the constant pairs of every env template of this warp
             P2 *t = stage + e * (2 * A + 4);
@@ -369,6 +387,8 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
     unsigned *vplain = reinterpret_cast<unsigned *>(smem + p.off_vlist);
     unsigned short *vspecial = reinterpret_cast<unsigned short *>(vplain + p.nvec_env);
     int *vcount = reinterpret_cast<int *>(smem + p.off_vlist + p.nvec_env * 6 + 8 - (p.nvec_env * 6) % 8);   // {plain, special}
+    int *vstart = vcount + 2;                                            // [n_chunks + 1] plain, [n_chunks + 1] special: list position of a chunk's first vector
+    uint16_t *slut = reinterpret_cast<uint16_t *>(vstart + 2 * (p.n_chunks + 1));   // [special vector][pair]: template pair that feeds it
     unsigned char *shifted = smem + p.off_shift + warp * 8 * p.shift_tst;
     const bool shift_rows = kShiftable && p.shift_tst > 0;
     if (shift_rows) {
@@ -384,11 +404,19 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
                 const unsigned below = (1u << T.lane) - 1u;
                 if (in_range && !special) vplain[n_plain + __popc(plain_mask & below)] = (unsigned)v | ((unsigned)(c * p.shift_tst + 2 * c + r0) << 16);
                 if (in_range && special) vspecial[n_special + __popc(special_mask & below)] = (unsigned short)v;
+                // (both lists are in vector order) a chunk's first vector: where the lists stand when the scan reaches it
+                if (in_range && v % p.img_vecs == 0) {
+                    vstart[v / p.img_vecs] = n_plain + __popc(plain_mask & below);
+                    vstart[p.n_chunks + 1 + v / p.img_vecs] = n_special + __popc(special_mask & below);
+                }
                 n_plain += __popc(plain_mask);
                 n_special += __popc(special_mask);
             }
-            if (T.lane == 0) { vcount[0] = n_plain; vcount[1] = n_special; }
+            if (T.lane == 0) { vcount[0] = n_plain; vcount[1] = n_special; vstart[p.n_chunks] = n_plain; vstart[2 * p.n_chunks + 1] = n_special; }
+            CCB_CHECK(n_special <= p.max_special);
         }
+        __syncthreads();
+        for (int i = threadIdx.x; i < vcount[1] * PPV; i += blockDim.x) slut[i] = (uint16_t)gather_index(p, vspecial[i / PPV] * PPV + i % PPV);
         // constant head of every copy: template bytes 2..5 = K1, K2 (bytes 0..1, pair 0, are never read from a copy)
         if (T.lane < 8) {
             unsigned char *t = shifted + T.lane * p.shift_tst + 2 * T.lane;
@@ -423,6 +451,9 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
         }
         walk[w] = bits;
     }
+    if (kMoves && LPE == 32 && p.cellmap_cells > 0)   // empty maps: no agent (0xFF) on any cell
+        for (int i = threadIdx.x; i < kWarpsPerCta * (2 * p.cellmap_cells + 128) / 4; i += blockDim.x)
+            reinterpret_cast<unsigned *>(smem + p.off_cellmap)[i] = 0xFFFFFFFFu;
     // statistics: arrivals and the reward sum change every step and stay in registers; the
     // episode-end sums are updated on the (rare) step an episode ends, in the warp's smem slot
     unsigned long long *red = red_all + warp * kStCount;
@@ -431,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
     unsigned st_arrivals = 0;
     double st_rsum = 0.0;
     int errbits = 0;
+    int img_slot = 0;   // next image of the warp's ring (int8 rows of big crews)
 
     // ---- per-lane constants ---------------------------------------------------------------------------
     int aidx[APL], aload[APL], ytoff[APL], rtoff[APL];
@@ -466,12 +498,26 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
         r.step = p.step[(int)m0 + tl];
         r.ep_ret = kMoves ? p.ep_ret[(int)m0 + tl] : 0.f;
     };
-    Record next;
     // (step launches alternate the direction: a launch starts on the groups the previous one wrote last, whose state is
     // still in L2)
+    auto group_of = [&](int w) { return (MODE == kModeStep && p.tpe_reverse) ? n_groups - 1 - w : w; };
+    // one env per warp (crews above 16): the record of the warp's NEXT env is requested before the current one is
+    // stepped — a warp works ~25k cycles on an env, and 13 % of its stall samples were this load (profiles/r2_ncu_summary.txt)
+    // (not with float32 rows: that mode is at the HBM roofline and measured 8 % slower with either change — the rows leave
+    // through st.global there, and warps that reach the row phase sooner only collide in the load/store pipe)
+    constexpr bool kPrefetch = CCB_LANES_PREFETCH && LPE == 32 && MODE == kModeStep && OBS != CC_OBS_FP32;
+    Record ahead;
+    {
+        const int gw0 = (int)blockIdx.x * kWarpsPerCta + warp;
+        if (kPrefetch && gw0 < n_groups) fetch(group_of(gw0), ahead);
+    }
     for (int gw = (int)blockIdx.x * kWarpsPerCta + warp; gw < n_groups; gw += total_warps) {
-        const int g = (MODE == kModeStep && p.tpe_reverse) ? n_groups - 1 - gw : gw;
-        fetch(g, next);
+        const int g = group_of(gw);
+        Record next;
+        if (kPrefetch) {
+            next = ahead;
+            if (gw + total_warps < n_groups) fetch(group_of(gw + total_warps), ahead);
+        } else fetch(g, next);
         const long long n0 = (long long)g * EPW;
         const int envs_here = (int)min((long long)EPW, p.n_envs - n0);
         const bool env_ok = T.tile < envs_here;           // false only in the ragged last group
@@ -608,7 +654,100 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
                     const unsigned occ = __ballot_sync(kFull, hit) & tile_bits;
                     if (T.li == l && !occ) cmp[s] = rq;                                     // :406-408
                 };
-                if (APL == 1 && A == LPE) {
+                // ---- one env per warp: the ordered turns resolved in PARALLEL --------------------------------------
+                // The reference moves agent 0, 1, 2, ... (collectivecrossing.py:197-202); agent i's move succeeds iff its
+                // target is free AT ITS TURN.  With every agent moving at most once that is decidable without the loop:
+                //   * a target that held an ACTIVE agent j at step start is free at turn i iff j < i and j's own move succeeded
+                //     (j > i has not moved yet; a j that does not move never leaves);
+                //   * among the agents that ask for one cell and are not ruled out by that, the FIRST in agent order enters,
+                //     all later ones find it taken.
+                // `own[cell]` (who stands there), `win[cell]` (first contender) and a status byte per agent live in shared
+                // memory; dependencies point to smaller agent indices only, so the chains end and are followed in rounds.
+                // Stacked ACTIVE agents (only injectable states) fall back to the sequential turns below.
+                bool sequential = true;
+                if constexpr (LPE == 32) {
+                    if (CCB_LANES_PARMOVES && OBS != CC_OBS_FP32 && p.cellmap_cells > 0) {
+                        unsigned char *own = smem + p.off_cellmap + warp * (2 * p.cellmap_cells + 128);
+                        unsigned char *win = own + p.cellmap_cells, *stat = win + p.cellmap_cells;
+                        enum { kFail = 0, kOk = 1, kUnknown = 2 };
+                        int tcell[APL];
+                        bool mover[APL], active[APL];
+#pragma unroll
+                        for (int k = 0; k < APL; ++k) {
+                            active[k] = cmp[k] != kGhost;
+                            mover[k] = req[k] != cmp[k];                                    // a request that passed the geometric test
+                            tcell[k] = cell[k] + ((action[k] & 1) ? PW : 1) * ((action[k] & 2) ? -1 : 1);
+                            CCB_CHECK(!active[k] || cell[k] < p.cellmap_cells);
+                            CCB_CHECK(!mover[k] || (tcell[k] >= 0 && tcell[k] < p.cellmap_cells));
+                            if (active[k]) own[cell[k]] = (unsigned char)aidx[k];
+                            stat[aidx[k]] = mover[k] ? kUnknown : kFail;
+                        }
+                        __syncwarp();
+                        bool stacked = false;
+#pragma unroll
+                        for (int k = 0; k < APL; ++k) stacked |= active[k] && own[cell[k]] != (unsigned char)aidx[k];
+                        if (!__any_sync(kFull, stacked)) {
+                            sequential = false;
+                            int dep[APL];
+                            bool cand[APL];
+#pragma unroll
+                            for (int k = 0; k < APL; ++k) {
+                                dep[k] = -1;
+                                cand[k] = mover[k];
+                                if (mover[k]) {
+                                    const int o = own[tcell[k]];
+                                    if (o != 0xFF) {
+                                        if (o > aidx[k] || stat[o] == kFail) cand[k] = false;   // still there at my turn / never leaves
+                                        else dep[k] = o;
+                                    }
+                                }
+                            }
+                            bool wrote;
+                            do {   // win[cell] = smallest agent index among the contenders (each round can only lower it)
+                                bool lower[APL];
+#pragma unroll
+                                for (int k = 0; k < APL; ++k) lower[k] = cand[k] && win[tcell[k]] > aidx[k];
+                                __syncwarp();
+                                wrote = false;
+#pragma unroll
+                                for (int k = 0; k < APL; ++k)
+                                    if (lower[k]) { win[tcell[k]] = (unsigned char)aidx[k]; wrote = true; }
+                                __syncwarp();
+                            } while (__any_sync(kFull, wrote));
+                            int st[APL];
+#pragma unroll
+                            for (int k = 0; k < APL; ++k) {
+                                st[k] = kFail;
+                                if (cand[k]) st[k] = win[tcell[k]] != aidx[k] ? kFail : (dep[k] < 0 ? kOk : kUnknown);
+                                if (mover[k]) stat[aidx[k]] = (unsigned char)st[k];
+                            }
+                            __syncwarp();
+                            bool changed;
+                            do {   // follow the chains: an agent that waits for j's cell succeeds iff j did
+                                int seen[APL];
+#pragma unroll
+                                for (int k = 0; k < APL; ++k) seen[k] = st[k] == kUnknown ? (int)stat[dep[k]] : (int)kUnknown;
+                                __syncwarp();
+                                changed = false;
+#pragma unroll
+                                for (int k = 0; k < APL; ++k)
+                                    if (st[k] == kUnknown && seen[k] != kUnknown) { st[k] = seen[k]; stat[aidx[k]] = (unsigned char)seen[k]; changed = true; }
+                                __syncwarp();
+                            } while (__any_sync(kFull, changed));
+#pragma unroll
+                            for (int k = 0; k < APL; ++k) {
+                                if (st[k] == kOk) cmp[k] = req[k];                           // :406-408
+                                if (cand[k]) win[tcell[k]] = 0xFF;                           // leave the map empty
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < APL; ++k)
+                            if (active[k]) own[cell[k]] = 0xFF;
+                        __syncwarp();
+                    }
+                }
+                if (!sequential) {
+                } else if (APL == 1 && A == LPE) {
 #pragma unroll
                     for (int l = 0; l < LPE; ++l) turn(0, l);
                 } else {
@@ -922,22 +1061,46 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
                 }
             } else if (shift_rows) {
                 if constexpr (kShiftable) {
-                    uint4 *outv = reinterpret_cast<uint4 *>(out);   // (the env block is a whole number of 16-byte vectors)
-                    const int n_plain = vcount[0], n_special = vcount[1];
-                    for (int idx = T.lane; idx < n_plain; idx += 32) {
-                        const unsigned e = vplain[idx];
-                        CCB_CHECK((int)(e & 0xffffu) < p.nvec_env && (int)(e >> 16) + 16 <= 8 * p.shift_tst && ((e >> 16) & 15u) == 0u);
-                        __stcs(outv + (e & 0xffffu), *reinterpret_cast<const uint4 *>(shifted + (e >> 16)));
-                    }
-                    for (int idx = T.lane; idx < n_special; idx += 32) {
-                        const int v = vspecial[idx];
-                        union { uint4 u; P2 e[PPV]; } pk;
-#pragma unroll
-                        for (int c = 0; c < PPV; ++c) {
-                            CCB_CHECK(v * PPV + c < p.lut_entries && lut[v * PPV + c] < p.stage_pairs);
-                            pk.e[c] = stage[lut[v * PPV + c]];
+                    // The env block leaves the SM chunk by chunk (8 rows = img_vecs vectors): the warp assembles a chunk in one of
+                    // kLaneImgRing shared-memory images — a plain vector is ONE aligned 16-byte load from the shifted template,
+                    // a special one is gathered pair by pair — and one lane hands the image to the TMA unit (cp.async.bulk).
+                    // Stores issued with st.global stall the SM's load/store pipe, and with it the other warps' shared-memory
+                    // work, whenever HBM pushes back (profiles/probes/lsu_coupling_probe.cu).
+                    unsigned char *ring = smem + p.off_img + warp * (kLaneImgRing * p.img_vecs * 16);
+                    unsigned char *dst = reinterpret_cast<unsigned char *>(out);
+                    const int chunk_bytes = p.img_vecs * 16;
+                    for (int c = 0; c < p.n_chunks; ++c) {
+                        unsigned char *img = ring + img_slot * chunk_bytes;
+                        img_slot ^= 1;
+                        if (T.lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kLaneImgRing - 1) : "memory");   // the copy that read this image is done
+                        __syncwarp();
+                        const int v0 = c * p.img_vecs;
+#pragma unroll kPlainUnroll
+                        for (int idx = vstart[c] + T.lane; idx < vstart[c + 1]; idx += 32) {
+                            const unsigned e = vplain[idx];
+                            CCB_CHECK((int)(e & 0xffffu) >= v0 && (int)(e & 0xffffu) < v0 + p.img_vecs && (int)(e >> 16) + 16 <= 8 * p.shift_tst && ((e >> 16) & 15u) == 0u);
+                            *reinterpret_cast<uint4 *>(img + ((e & 0xffffu) - v0) * 16) = *reinterpret_cast<const uint4 *>(shifted + (e >> 16));
                         }
-                        __stcs(outv + v, pk.u);
+                        for (int idx = vstart[p.n_chunks + 1 + c] + T.lane; idx < vstart[p.n_chunks + 2 + c]; idx += 32) {
+                            const int v = vspecial[idx];
+                            union { uint4 u; P2 e[PPV]; } pk;
+#pragma unroll
+                            for (int q = 0; q < PPV; ++q) {
+                                CCB_CHECK(idx < p.max_special && slut[idx * PPV + q] < p.stage_pairs);
+                                pk.e[q] = stage[slut[idx * PPV + q]];
+                            }
+                            CCB_CHECK(v >= v0 && v < v0 + p.img_vecs);
+                            *reinterpret_cast<uint4 *>(img + (v - v0) * 16) = pk.u;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy read
+                        __syncwarp();
+                        if (T.lane == 0) {
+                            unsigned long long l2_evict_first;
+                            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_evict_first));
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                                         ::"l"(dst + (size_t)c * chunk_bytes), "r"((unsigned)__cvta_generic_to_shared(img)), "r"((unsigned)chunk_bytes), "l"(l2_evict_first) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
                     }
                 }
             } else if (cached) {
@@ -951,6 +1114,7 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
         }
     }
 
+    if (kShiftable && T.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until the copies are done
     // ---- statistics: per-warp slots in shared memory -> one atomic per slot per CTA ----------------
     if (MODE == kModeStep) {
         // every lane counted arrivals warp-wide: lane 0's copy is the warp's count
