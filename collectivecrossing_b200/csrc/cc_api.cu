@@ -96,15 +96,22 @@ void fill_params(const cc_handle *h, KParams &p, int obs_dtype, bool needs_bitma
     off += (rows && h->lpe <= 16) ? ccb::kDescWords * 4 * ccb::kThreads : 0;
     if (shifted) {
         p.nvec_env = env_bytes / 16;
-        p.shift_tst = round_up(14 + (2 * A + 4) * 2 + 16, 16);
+        p.shift_tst = round_up(14 + (6 + 4 * A) + 18, 16);   // shift + row template + its first 16 bytes again (+ agent 2's block)
         p.off_shift = off;
         off += ccb::kWarpsPerCta * 8 * p.shift_tst;
         // a row is 6 + 4A = 2 x odd bytes: 8 rows are the smallest run of rows that is a whole number of 16-byte vectors
-        p.img_vecs = (6 + 4 * A) / 2;
-        p.n_chunks = A / 8;                       // env_bytes % 16 == 0 <=> A % 8 == 0
-        p.max_special = 4 * A + 8;                // per row at most: a straddling vector, a head vector, two that touch the own block
-        p.off_vlist = off;
-        off += round_up(p.nvec_env * 6 + 16 + 2 * (p.n_chunks + 1) * 4 + p.max_special * 16, 16);
+        // (env_bytes % 16 == 0 <=> A % 8 == 0); chunks of 8 m rows, about 2.5 KB: small chunks pay a fence and three warp syncs each
+        const int bytes8 = 8 * (6 + 4 * A);
+        int m = (2560 + bytes8 / 2) / bytes8;
+        if (m < 1) m = 1;
+        if (8 * m > 32) m = 4;                    // one lane patches one row
+        if (8 * m > A) m = A / 8;
+        p.img_rows = 8 * m;
+        p.img_vecs = m * bytes8 / 16;
+        p.n_chunks = (A + p.img_rows - 1) / p.img_rows;
+        p.max_special = 0;
+        p.off_vlist = off;                        // source offsets of a chunk's vectors (uint32)
+        off += round_up(p.img_vecs * 4, 16);
         p.off_img = off;
         off += ccb::kWarpsPerCta * ccb::kLaneImgRing * p.img_vecs * 16;
     }

@@ -16,7 +16,7 @@
 #include "../../include/ccb200.h"
 
 #ifndef CCB_MIN_BLOCKS_APL2
-#define CCB_MIN_BLOCKS_APL2 1   // crews of 33-64 agents (two agents per lane): 108 registers, 2 CTAs per SM (3 CTAs at 76 registers measured slower: 1.63 vs 1.49 ms int8, 3.04 vs 2.77 ms float32 per 262 k envs)
+#define CCB_MIN_BLOCKS_APL2 2   // crews of 33-64 agents (two agents per lane): at most 128 registers, 2 CTAs per SM (3 CTAs at 76 registers measured slower: 1.63 vs 1.49 ms int8, 3.04 vs 2.77 ms float32 per 262 k envs)
 #endif
 #ifndef CCB_LANES_PREFETCH
 #define CCB_LANES_PREFETCH 1   // one env per warp: request the next env's record before stepping the current one
@@ -44,7 +44,11 @@
 namespace ccb {
 
 constexpr int kPlainUnroll = CCB_LANES_UNROLL;
-constexpr int kLaneImgRing = 2;   // chunk images per warp (int8 rows of big crews)
+#ifndef CCB_LANE_IMG_RING
+#define CCB_LANE_IMG_RING 2
+#endif
+constexpr int kMaxImgIter = 9;    // an 8-row chunk of the largest crew (128 agents) is 259 vectors = 9 per lane
+constexpr int kLaneImgRing = CCB_LANE_IMG_RING;   // chunk images per warp (int8 rows of big crews)
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -100,7 +104,8 @@ struct KParams {
     int shift_tst;                // bytes of one shifted copy (multiple of 16)
     int off_shift;                // [warp][8][shift_tst]
     int off_vlist;                // unsigned plain[nvec_env], unsigned short special[nvec_env], counts[2], starts[2][n_chunks+1], special LUT
-    int img_vecs, n_chunks;       // the env block leaves the SM in n_chunks bulk copies of img_vecs vectors (8 rows: a multiple of 16 bytes)
+    int img_vecs, n_chunks;       // the env block leaves the SM in n_chunks bulk copies of (at most) img_vecs vectors = img_rows rows
+    int img_rows;                 // rows per chunk: a multiple of 8 (8 rows are the smallest run of rows that is whole 16-byte vectors)
     int off_img;                  // [warp][kLaneImgRing][img_vecs * 16] image ring
     int max_special;              // rows of the special-vector LUT
     int nvec_env;                 // 16-byte vectors of an env's observation block
@@ -321,7 +326,8 @@ __device__ __forceinline__ int greedy_decision(int row, unsigned vmask) {
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
 template <int LPE, int APL, int OBS, int MODE>
-__global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 ? CCB_MIN_BLOCKS : (APL == 2 ? CCB_MIN_BLOCKS_APL2 : 1))) cc_kernel(const __grid_constant__ KParams p) {
+// (two agents per lane: the float32-row instantiation keeps its registers — 122, measured 8 % faster than capped at 128 / 2 CTAs)
+__global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 ? CCB_MIN_BLOCKS : (APL == 2 ? (OBS == CC_OBS_FP32 ? 1 : CCB_MIN_BLOCKS_APL2) : 1))) cc_kernel(const __grid_constant__ KParams p) {
     using TL_ = Tile<LPE, APL>;
     using OT = typename std::conditional<OBS == CC_OBS_FP32, float, int8_t>::type;
     using P2 = typename PairOf<OT>::type;
@@ -378,49 +384,27 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
             t[0] = mk_pair<OT>(0, 0); t[1] = mk_pair<OT>(p.DC, p.D); t[2] = mk_pair<OT>(p.DL, p.DR); t[2 * A + 3] = mk_pair<OT>(-1, -1);
         }
     }
-    // int8 rows of big crews: classify the env block's 16-byte vectors once.  Row i of an env is the row template
-    // [P K1 K2 S_0a ... S_(A-1)b] with pair 0 replaced by S_ia and the own block by M, so a vector that lies inside
-    // one row and touches neither pair 0 nor the own block is 16 consecutive template bytes: it is loaded with one
-    // aligned 16-byte load from the copy of the template whose shift matches the row's alignment ("plain" list:
-    // vector | offset << 16).  The others ("special" list) are gathered pair by pair through the LUT.
+    // int8 rows of big crews (one env per warp).  Row i of an env is the row template [P K1 K2 S_0a ... S_(A-1)b] with pair 0
+    // replaced by S_ia and the own block by M; a row is 6 + 4A = 2 x odd bytes, so rows start at every even alignment.  The warp
+    // keeps 8 copies of the template, copy c shifted by 2c bytes, each followed by the first 16 bytes of the template again:
+    // ANY 16-byte vector of the output — also one that straddles two rows — is then 16 consecutive bytes of the copy whose
+    // shift matches, i.e. ONE aligned 16-byte load, up to the bytes that differ from row to row (pair 0 and the own block),
+    // which are patched in the assembled image.  img_src[j] = offset of the source of vector j of an 8-row chunk.
     constexpr bool kShiftable = kHasObs && OBS == CC_OBS_INT8 && LPE == 32 && MODE != kModeReset;
-    unsigned *vplain = reinterpret_cast<unsigned *>(smem + p.off_vlist);
-    unsigned short *vspecial = reinterpret_cast<unsigned short *>(vplain + p.nvec_env);
-    int *vcount = reinterpret_cast<int *>(smem + p.off_vlist + p.nvec_env * 6 + 8 - (p.nvec_env * 6) % 8);   // {plain, special}
-    int *vstart = vcount + 2;                                            // [n_chunks + 1] plain, [n_chunks + 1] special: list position of a chunk's first vector
-    uint16_t *slut = reinterpret_cast<uint16_t *>(vstart + 2 * (p.n_chunks + 1));   // [special vector][pair]: template pair that feeds it
     unsigned char *shifted = smem + p.off_shift + warp * 8 * p.shift_tst;
     const bool shift_rows = kShiftable && p.shift_tst > 0;
+    const int lrow = 6 + 4 * A;
+    unsigned *img_src = reinterpret_cast<unsigned *>(smem + p.off_vlist);   // [vector of a chunk]: where its 16 bytes lie in the shifted copies
     if (shift_rows) {
-        const int lrow = 6 + 4 * A;
-        if (warp == 0) {
-            int n_plain = 0, n_special = 0;
-            for (int v0 = 0; v0 < p.nvec_env; v0 += 32) {
-                const int v = v0 + T.lane, b0 = 16 * v, i0 = b0 / lrow, r0 = b0 - i0 * lrow;
-                const bool in_range = v < p.nvec_env;
-                const bool special = (b0 + 15) / lrow != i0 || r0 < 2 || (r0 < 10 + 4 * i0 && r0 + 16 > 6 + 4 * i0);
-                const int c = ((16 - (r0 & 15)) >> 1) & 7;                     // copy whose shift aligns template byte r0
-                const unsigned plain_mask = __ballot_sync(kFull, in_range && !special), special_mask = __ballot_sync(kFull, in_range && special);
-                const unsigned below = (1u << T.lane) - 1u;
-                if (in_range && !special) vplain[n_plain + __popc(plain_mask & below)] = (unsigned)v | ((unsigned)(c * p.shift_tst + 2 * c + r0) << 16);
-                if (in_range && special) vspecial[n_special + __popc(special_mask & below)] = (unsigned short)v;
-                // (both lists are in vector order) a chunk's first vector: where the lists stand when the scan reaches it
-                if (in_range && v % p.img_vecs == 0) {
-                    vstart[v / p.img_vecs] = n_plain + __popc(plain_mask & below);
-                    vstart[p.n_chunks + 1 + v / p.img_vecs] = n_special + __popc(special_mask & below);
-                }
-                n_plain += __popc(plain_mask);
-                n_special += __popc(special_mask);
-            }
-            if (T.lane == 0) { vcount[0] = n_plain; vcount[1] = n_special; vstart[p.n_chunks] = n_plain; vstart[2 * p.n_chunks + 1] = n_special; }
-            CCB_CHECK(n_special <= p.max_special);
+        for (int j = threadIdx.x; j < p.img_vecs; j += blockDim.x) {
+            const int b0 = 16 * j, r0 = b0 % lrow, c = ((16 - (r0 & 15)) >> 1) & 7;   // copy whose shift aligns template byte r0
+            img_src[j] = (unsigned)(c * p.shift_tst + 2 * c + r0);
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < vcount[1] * PPV; i += blockDim.x) slut[i] = (uint16_t)gather_index(p, vspecial[i / PPV] * PPV + i % PPV);
-        // constant head of every copy: template bytes 2..5 = K1, K2 (bytes 0..1, pair 0, are never read from a copy)
+        // constant head of every copy and of its 16-byte tail: template bytes 2..5 = K1, K2 (bytes 0..1, pair 0, are patched)
         if (T.lane < 8) {
             unsigned char *t = shifted + T.lane * p.shift_tst + 2 * T.lane;
-            t[2] = (unsigned char)p.DC; t[3] = (unsigned char)p.D; t[4] = (unsigned char)p.DL; t[5] = (unsigned char)p.DR;
+            t[2] = t[lrow + 2] = (unsigned char)p.DC; t[3] = t[lrow + 3] = (unsigned char)p.D;
+            t[4] = t[lrow + 4] = (unsigned char)p.DL; t[5] = t[lrow + 5] = (unsigned char)p.DR;
         }
     }
     for (int i = threadIdx.x; i < PW; i += blockDim.x) xt[i] = make_xt(p, i - 1);
@@ -463,6 +447,8 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
     double st_rsum = 0.0;
     int errbits = 0;
     int img_slot = 0;   // next image of the warp's ring (int8 rows of big crews)
+    unsigned long long l2_evict_first = 0;   // (the rows are written once and not read by this kernel)
+    if (kHasObs && OBS == CC_OBS_INT8 && LPE == 32) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_evict_first));
 
     // ---- per-lane constants ---------------------------------------------------------------------------
     int aidx[APL], aload[APL], ytoff[APL], rtoff[APL];
@@ -1013,6 +999,10 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
                             unsigned char *d = shifted + c * p.shift_tst + 2 * c + 6 + 4 * aidx[k];
                             if (c & 1) *reinterpret_cast<unsigned *>(d) = lo | (hi << 16);
                             else { *reinterpret_cast<unsigned short *>(d) = (unsigned short)lo; *reinterpret_cast<unsigned short *>(d + 2) = (unsigned short)hi; }
+                            if (aidx[k] < 3) {   // the 16-byte tail repeats the head of the template (a row is 2 mod 4 bytes long)
+                                unsigned char *d2 = d + lrow;
+                                *reinterpret_cast<unsigned short *>(d2) = (unsigned short)lo; *reinterpret_cast<unsigned short *>(d2 + 2) = (unsigned short)hi;
+                            }
                         }
                     }
                 }
@@ -1066,39 +1056,42 @@ __global__ void __launch_bounds__(kThreads, (MODE != kModeStep) ? 1 : (APL == 1 
                     // a special one is gathered pair by pair — and one lane hands the image to the TMA unit (cp.async.bulk).
                     // Stores issued with st.global stall the SM's load/store pipe, and with it the other warps' shared-memory
                     // work, whenever HBM pushes back (profiles/probes/lsu_coupling_probe.cu).
-                    unsigned char *ring = smem + p.off_img + warp * (kLaneImgRing * p.img_vecs * 16);
+                    // (32-bit shared-memory addresses: the copy of a vector is its source offset (ld.shared.u32), one ld.shared.v4 and one st.shared.v4)
+                    const unsigned src_s = (unsigned)__cvta_generic_to_shared(img_src) + 4u * (unsigned)T.lane;
+                    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(smem + p.off_img + warp * (kLaneImgRing * p.img_vecs * 16));
+                    const unsigned shifted_s = (unsigned)__cvta_generic_to_shared(shifted);
                     unsigned char *dst = reinterpret_cast<unsigned char *>(out);
-                    const int chunk_bytes = p.img_vecs * 16;
+                    const unsigned chunk_bytes = (unsigned)p.img_vecs * 16u;
                     for (int c = 0; c < p.n_chunks; ++c) {
-                        unsigned char *img = ring + img_slot * chunk_bytes;
-                        img_slot ^= 1;
+                        const unsigned img_s = ring_s + (unsigned)img_slot * chunk_bytes;
+                        img_slot = img_slot + 1 == kLaneImgRing ? 0 : img_slot + 1;
+                        const int rows_here = min(p.img_rows, A - c * p.img_rows);          // (the last chunk may be shorter)
+                        const int vecs_here = rows_here * lrow / 16;
                         if (T.lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kLaneImgRing - 1) : "memory");   // the copy that read this image is done
                         __syncwarp();
-                        const int v0 = c * p.img_vecs;
-#pragma unroll kPlainUnroll
-                        for (int idx = vstart[c] + T.lane; idx < vstart[c + 1]; idx += 32) {
-                            const unsigned e = vplain[idx];
-                            CCB_CHECK((int)(e & 0xffffu) >= v0 && (int)(e & 0xffffu) < v0 + p.img_vecs && (int)(e >> 16) + 16 <= 8 * p.shift_tst && ((e >> 16) & 15u) == 0u);
-                            *reinterpret_cast<uint4 *>(img + ((e & 0xffffu) - v0) * 16) = *reinterpret_cast<const uint4 *>(shifted + (e >> 16));
-                        }
-                        for (int idx = vstart[p.n_chunks + 1 + c] + T.lane; idx < vstart[p.n_chunks + 2 + c]; idx += 32) {
-                            const int v = vspecial[idx];
-                            union { uint4 u; P2 e[PPV]; } pk;
 #pragma unroll
-                            for (int q = 0; q < PPV; ++q) {
-                                CCB_CHECK(idx < p.max_special && slut[idx * PPV + q] < p.stage_pairs);
-                                pk.e[q] = stage[slut[idx * PPV + q]];
+                        for (int k = 0; k < kMaxImgIter; ++k)
+                            if (T.lane + 32 * k < vecs_here) {
+                                uint4 v;
+                                unsigned so;
+                                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(so) : "r"(src_s + 128u * k));
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(shifted_s + so));
+                                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(img_s + 16u * (unsigned)(T.lane + 32 * k)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                             }
-                            CCB_CHECK(v >= v0 && v < v0 + p.img_vecs);
-                            *reinterpret_cast<uint4 *>(img + (v - v0) * 16) = pk.u;
+                        __syncwarp();
+                        if (T.lane < rows_here) {   // row i of the env: own position in front, -1 over the own block (observations.py:62-64,92-93)
+                            const int i = c * p.img_rows + T.lane;
+                            const unsigned row_s = img_s + (unsigned)(T.lane * lrow);
+                            const unsigned short own = *reinterpret_cast<const unsigned short *>(stage + 3 + 2 * i);
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(row_s), "h"(own) : "memory");
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(row_s + 6u + 4u * (unsigned)i), "h"((unsigned short)0xffffu) : "memory");
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(row_s + 8u + 4u * (unsigned)i), "h"((unsigned short)0xffffu) : "memory");
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy read
                         __syncwarp();
                         if (T.lane == 0) {
-                            unsigned long long l2_evict_first;
-                            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_evict_first));
                             asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                                         ::"l"(dst + (size_t)c * chunk_bytes), "r"((unsigned)__cvta_generic_to_shared(img)), "r"((unsigned)chunk_bytes), "l"(l2_evict_first) : "memory");
+                                         ::"l"(dst + (size_t)c * chunk_bytes), "r"(img_s), "r"((unsigned)vecs_here * 16u), "l"(l2_evict_first) : "memory");
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                     }
