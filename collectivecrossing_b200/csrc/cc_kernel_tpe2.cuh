@@ -57,8 +57,15 @@ struct T2Layout {
     static constexpr bool kImage = OBS == CC_OBS_INT8;                 // 8 agents: an env's block is 19 x 16 bytes
     static constexpr int kEnvBytes = A * (6 + 4 * A);
     static constexpr int kImageBytes = kImage ? 32 * kEnvBytes : 0;    // 9,728 B: the warp's 32 blocks, contiguous like the output
-    // the policy bitmap aliases the image (idle while the warp steps)
-    static constexpr int kBytesPerWarp = kImageBytes > kT2BitmapBytesPerWarp ? kImageBytes : kT2BitmapBytesPerWarp;
+    // float32 rows (even crews): the row templates + image ring of cc_kernel_tpe.cuh, emitted by tpe_emit_group_tma
+    using L1 = TpeLayout<A, CC_OBS_FP32>;
+    static constexpr bool kRows32 = OBS == CC_OBS_FP32;
+    static constexpr int kRows32Bytes = kRows32 ? L1::kStageBytesPerWarp : 0;
+    // the policy bitmap aliases the image / the image ring (idle while the warp steps): it is zeroed before every use there
+    static constexpr bool kDirtyBitmap = kImage || kRows32;
+    static constexpr int kBitmapOffset = kRows32 ? L1::kTplBytesPerWarp : 0;
+    static constexpr int kBytesNeeded = kImage ? kImageBytes : (kRows32 ? kRows32Bytes : 0);
+    static constexpr int kBytesPerWarp = kBytesNeeded > kBitmapOffset + kT2BitmapBytesPerWarp ? kBytesNeeded : kBitmapOffset + kT2BitmapBytesPerWarp;
     static constexpr int kDynBytes = kT2Warps * kBytesPerWarp;
 };
 
@@ -155,7 +162,9 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
     using L = T2Layout<A, OBS>;
     const int B = BT >= 0 ? BT : p.B;
     static_assert(A >= 1 && A <= 8, "thread-per-env mapping is for crews of at most 8");
-    static_assert(OBS == CC_OBS_NONE || OBS == CC_OBS_TABLE || (OBS == CC_OBS_INT8 && A == 8), "float32 rows: cc_step_tpe_kernel");
+    static_assert(OBS == CC_OBS_NONE || OBS == CC_OBS_TABLE || (OBS == CC_OBS_INT8 && A == 8) || (OBS == CC_OBS_FP32 && A % 2 == 0),
+                  "int8 rows: 8 agents; float32 rows: even crews (an env's block must be whole 16-byte vectors for the bulk copies)");
+    static_assert(!L::kRows32 || L::L1::kTma, "float32 rows leave through the TMA image ring");
     constexpr unsigned kOnes = 0x01010101u;
     // byte lanes of the agents that exist (k < A)
     constexpr unsigned kM0 = A >= 4 ? kOnes : (kOnes >> (8 * (4 - A)));
@@ -171,6 +180,22 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
     for (int i = threadIdx.x; i < (int)(sizeof(T2Tables) / 16); i += blockDim.x)
         reinterpret_cast<uint4 *>(&tb)[i] = static_cast<const uint4 *>(p.t2_tables)[i];
     for (int i = threadIdx.x; i < L::kDynBytes / 4; i += blockDim.x) reinterpret_cast<unsigned *>(smem)[i] = 0u;
+    __shared__ __align__(16) unsigned lut[L::kRows32 ? L::L1::kLutWords : 4];   // float32 rows: emission table of tpe_emit_group_tma
+    if constexpr (L::kRows32) {
+        __syncthreads();   // (the zero fill above must not overtake the constants below)
+        using L1 = typename L::L1;
+        for (int w = threadIdx.x; w < L1::kLutWords; w += blockDim.x) {
+            // entry (j, lane): pair w = lane + 32 j of ANY env (offset inside that env's template)
+            const int src = w < L1::PPE ? tpe_source<A>(w / L1::R, w % L1::R) : kSrcM;
+            lut[w] = src >= 0 ? (unsigned)(src * L1::PSZ) : (0x80000000u | (unsigned)(-src));
+        }
+        // the constant pairs of this thread's template
+        float2 *t = reinterpret_cast<float2 *>(smem + warp * L::kBytesPerWarp + lane * L1::TSB);
+        t[2 * A] = make_float2((float)p.DC, (float)p.D); t[2 * A + 1] = make_float2((float)p.DL, (float)p.DR); t[2 * A + 2] = make_float2(-1.f, -1.f);
+    }
+    const TpeConstPairs kc = {make_uint2(__float_as_uint((float)p.DC), __float_as_uint((float)p.D)),
+                              make_uint2(__float_as_uint((float)p.DL), __float_as_uint((float)p.DR)),
+                              make_uint2(__float_as_uint(-1.f), __float_as_uint(-1.f))};
     unsigned long long *red = red_all + warp * kStCount;
     if (lane < kStCount) red[lane] = 0ull;
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.tpe_counter_next = 0u;   // the counter the NEXT launch uses
@@ -180,7 +205,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                    dc_s = (unsigned)__cvta_generic_to_shared(tb.dcell);
     unsigned char *wsmem = smem + warp * L::kBytesPerWarp;
     const unsigned img_s = (unsigned)__cvta_generic_to_shared(wsmem);
-    const unsigned bm = img_s + 4u * lane;                      // this thread's bitmap row r at bm + 128 r
+    const unsigned bm = img_s + (unsigned)L::kBitmapOffset + 4u * lane;   // this thread's bitmap row r at bm + 128 r
     unsigned tbase[A];                                          // table base of agent k's type
 #pragma unroll
     for (int k = 0; k < A; ++k) tbase[k] = tab_s + (k < B ? 0u : 8u);
@@ -259,12 +284,12 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
         } else {
             // ---- baseline_policies/greedy_policy.py:64-88, waiting_policy.py:62-131 at randomness_factor 0 ----------
             // occupancy of the padded lattice, one word per row, private to the thread (walls are in the table)
-            if constexpr (L::kImage) {   // the image the bitmap aliases must have been read by the previous group's copy
+            if constexpr (L::kDirtyBitmap) {   // the image(s) the bitmap aliases must have been read by the previous group's copies
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
             }
             // (the bitmap is clean: zeroed at kernel start and after every use; where it aliases the image, zeroed here)
-            if constexpr (L::kImage) {
+            if constexpr (L::kDirtyBitmap) {
 #pragma unroll
                 for (int r = 0; r < kT2MaxRows; ++r)
                     if (r < PH) sts32(bm + 128u * r, 0u);
@@ -298,7 +323,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
                 const unsigned m = t2_fill(k < 4 ? go7[0] : go7[1], k & 3);
                 act[k] = ((a ^ (unsigned)CC_ACT_WAIT) & m) ^ (unsigned)CC_ACT_WAIT;
             }
-            if constexpr (!L::kImage) {
+            if constexpr (!L::kDirtyBitmap) {
 #pragma unroll
                 for (int k = 0; k < A; ++k)
                     if ((fl[k >> 2] >> (8 * (k & 3))) & 1u) sts32(arow[k], 0u);
@@ -468,7 +493,20 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
         if (env_ok) __stcs(reinterpret_cast<unsigned char *>(p.env_flags) + (size_t)tt * (size_t)p.slice_envs + n, (unsigned char)eflags);
 
         // ---- observations.py:43-94 from the post-step (post-reset) state ----------------------------------------------------
-        if constexpr (OBS != CC_OBS_NONE) {
+        if constexpr (OBS == CC_OBS_FP32) {
+            // the env's row template [S_0a S_0b ... K1 K2 M] (cc_kernel_tpe.cuh), then the warp's 32 blocks through the TMA image ring
+            using L1 = typename L::L1;
+            float2 *tpl = reinterpret_cast<float2 *>(wsmem + lane * L1::TSB);
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                tpl[2 * k] = make_float2((float)(int)((e[k].x >> 8) & 0xffu), (float)(int)((e[k].x >> 16) & 0xfu));
+                tpl[2 * k + 1] = make_float2(k < B ? 0.f : 1.f, (float)(int)(((k < 4 ? fl[0] : fl[1]) >> (8 * (k & 3))) & 1u));
+            }
+            __syncwarp();
+            void *obs_t = static_cast<unsigned char *>(p.obs) + (size_t)tt * (size_t)p.slice_obs_bytes;
+            tpe_emit_group_tma<A, CC_OBS_FP32>(lut, img_s, obs_t, g, envs_here, lane, kc);
+            __syncwarp();
+        } else if constexpr (OBS != CC_OBS_NONE) {
             // T_k = (x_k, y_k, type_k, active_k): the agent's block of every row (observations.py:80-91)
             unsigned T[A];
 #pragma unroll
@@ -546,7 +584,7 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
 #endif
     }
 
-    if (L::kImage && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until the copies are done
+    if (L::kDirtyBitmap && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until the copies are done
     // ---- statistics: per-warp slots in shared memory -> one atomic per slot per CTA -----------------------------------------
     {
         double rs = st_rsum;

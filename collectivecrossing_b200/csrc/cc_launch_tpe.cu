@@ -85,7 +85,9 @@ int launch_tpe2_t(cc_handle *h, KParams p, cudaStream_t s) {
 bool tpe2_eligible(const KParams &p, int obs_dtype) {
     static const bool enabled = [] { const char *v = std::getenv("CCB200_TPE2"); return !(v && v[0] == '0'); }();
     const int PW = p.W + 3, PH = p.H + 3;
-    return enabled && obs_dtype != CC_OBS_FP32 && PW <= ccb::kT2MaxCols && PH <= ccb::kT2MaxRows && PW * PH <= ccb::kT2MaxCells;
+    static const bool rows32 = [] { const char *v = std::getenv("CCB200_TPE2_FP32"); return !(v && v[0] == '0'); }();   // (A/B switch)
+    if (obs_dtype == CC_OBS_FP32 && (!rows32 || p.A % 2 != 0)) return false;   // float32 rows of odd crews: cc_step_tpe_kernel
+    return enabled && PW <= ccb::kT2MaxCols && PH <= ccb::kT2MaxRows && PW * PH <= ccb::kT2MaxCells;
 }
 
 }  // namespace
@@ -93,6 +95,9 @@ bool tpe2_eligible(const KParams &p, int obs_dtype) {
 #define CCB_TPE2_CASES(A_)                                                                  \
     case A_ * 32 + CC_OBS_NONE: return launch_tpe2_t<A_, CC_OBS_NONE>(h, p, s);                 \
     case A_ * 32 + CC_OBS_TABLE: return launch_tpe2_t<A_, CC_OBS_TABLE>(h, p, s);
+#define CCB_TPE2_CASES_EVEN(A_)                                                             \
+    CCB_TPE2_CASES(A_)                                                                      \
+    case A_ * 32 + CC_OBS_FP32: return launch_tpe2_t<A_, CC_OBS_FP32>(h, p, s);
 #define CCB_TPE_CASES(A_)                                                                   \
     case A_ * 32 + CC_OBS_NONE: return launch_tpe_t<A_, CC_OBS_NONE>(h, p, s);                  \
     case A_ * 32 + CC_OBS_TABLE: return launch_tpe_t<A_, CC_OBS_TABLE>(h, p, s);                \
@@ -101,7 +106,7 @@ bool tpe2_eligible(const KParams &p, int obs_dtype) {
 #if CCB_TPE_PART == 0
 int cc_launch_tpe_part0(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s) {
     if (tpe2_eligible(p, obs_dtype)) {
-        switch (p.A * 32 + obs_dtype) { CCB_TPE2_CASES(1) CCB_TPE2_CASES(2) CCB_TPE2_CASES(3) CCB_TPE2_CASES(4) }
+        switch (p.A * 32 + obs_dtype) { CCB_TPE2_CASES(1) CCB_TPE2_CASES_EVEN(2) CCB_TPE2_CASES(3) CCB_TPE2_CASES_EVEN(4) }
     }
     switch (p.A * 32 + obs_dtype) {
         CCB_TPE_CASES(1) CCB_TPE_CASES(2) CCB_TPE_CASES(3) CCB_TPE_CASES(4)
@@ -130,10 +135,11 @@ int cc_launch_tpe(cc_handle *h, const KParams &p, int obs_dtype, cudaStream_t s)
             case CC_OBS_NONE: return launch_tpe2_t<8, CC_OBS_NONE, 5>(h, p, s);
             case CC_OBS_TABLE: return launch_tpe2_t<8, CC_OBS_TABLE, 5>(h, p, s);
             case CC_OBS_INT8: return launch_tpe2_t<8, CC_OBS_INT8, 5>(h, p, s);
+            case CC_OBS_FP32: return launch_tpe2_t<8, CC_OBS_FP32, 5>(h, p, s);
             }
         }
         switch (p.A * 32 + obs_dtype) {
-            CCB_TPE2_CASES(5) CCB_TPE2_CASES(6) CCB_TPE2_CASES(7) CCB_TPE2_CASES(8)
+            CCB_TPE2_CASES(5) CCB_TPE2_CASES_EVEN(6) CCB_TPE2_CASES(7) CCB_TPE2_CASES_EVEN(8)
         case 8 * 32 + CC_OBS_INT8: return launch_tpe2_t<8, CC_OBS_INT8>(h, p, s);
         }
     }

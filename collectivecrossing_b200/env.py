@@ -60,7 +60,8 @@ class CollectiveCrossingEnv(_Base):
                                               auto_reset=False, with_info=True)
         self._host = self._dev.make_host_buffers(pinned=False)
         self._host["order"] = torch.zeros((1, len(self._ids)), dtype=torch.int8)
-        self._np_random: np.random.Generator | None = None  # only for user code that samples from it
+        # the env's generator lives on the device (cc_reset_seeded); `np_random` hands out a numpy view of it (see the property)
+        self._np_random: np.random.Generator | None = None
         # the reference's strategy objects (collectivecrossing.py:69-78); their values come from the device
         from .observations import get_observation_function
         from .rewards import get_reward_function
@@ -114,9 +115,34 @@ class CollectiveCrossingEnv(_Base):
 
     @property
     def np_random(self) -> np.random.Generator:
+        """gymnasium's ``env.np_random``: in the reference THE generator ``reset()`` places agents with
+        (collectivecrossing.py:95,105-106,134-137).  Here that generator lives on the device; this property returns a numpy
+        ``Generator(PCG64)`` set to the device generator's current state, and the next unseeded ``reset()`` pushes the state
+        back first — so user code that draws from ``env.np_random`` between resets shifts the placement stream exactly as it
+        does in the reference."""
+        if not getattr(self, "_seeded", False):   # gymnasium seeds from OS entropy on first use; the next reset() takes it over
+            self._np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence()))
+            self._seeded = True
         if self._np_random is None:
-            self._np_random = np.random.default_rng()
+            raw = self._dev.get_state()["rng"].cpu().numpy().astype(np.uint64)[0]      # hi, lo, inc hi, inc lo, buffered, has_buffered
+            bg = np.random.PCG64()
+            bg.state = {"bit_generator": "PCG64", "state": {"state": (int(raw[0]) << 64) | int(raw[1]), "inc": (int(raw[2]) << 64) | int(raw[3])},
+                        "has_uint32": int(raw[5]), "uinteger": int(raw[4])}
+            self._np_random = np.random.Generator(bg)
         return self._np_random
+
+    def _push_np_random(self) -> None:
+        """The host view of the generator (if one was handed out) back to the device, before the device draws from it."""
+        if self._np_random is None:
+            return
+        st = self._np_random.bit_generator.state
+        m = (1 << 64) - 1
+        raw = np.array([[st["state"]["state"] >> 64, st["state"]["state"] & m, st["state"]["inc"] >> 64, st["state"]["inc"] & m,
+                         st["uinteger"], st["has_uint32"]]], dtype=np.uint64)
+        state = self._dev.get_state()
+        state["rng"] = torch.from_numpy(raw.view(np.int64)).to(self._dev.device)
+        self._dev.load_state(state)
+        self._np_random = None
 
     def close(self) -> None:
         self._dev.close()
@@ -191,10 +217,11 @@ class CollectiveCrossingEnv(_Base):
         if seed is not None:
             if not 0 <= int(seed) < 2**63:
                 raise ValueError("seed must be a non-negative integer below 2**63")
-            self._np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(int(seed))))
+            self._np_random = None      # a fresh generator, like gymnasium's reset(seed=...)
             obs = self._dev.reset_seeded(torch.tensor([int(seed)], dtype=torch.int64, device=self._dev.device))
             self._seeded = True
         else:
+            self._push_np_random()      # draws the caller made from env.np_random count, like in the reference
             obs = self._dev.reset_seeded(None)  # keep drawing from the env's generator, like gymnasium
         self._dev.check_error()
         self._agents = self._create_dummy_agents()

@@ -73,7 +73,7 @@ def test_config4_four_million_envs_reward_sweep(reward, kw):
     n = 1 << 22
     offsets = [0, 777_777, n // 2 + 31, n - 64]
     resets, st, name = _strided_oracle_check(readme_config(reward, "individual", 100, **kw), n, "float32", "random", 125, 64, offsets)
-    assert name == "ccb::cc_step_tpe_kernel<8,4>"
+    assert name == "ccb::cc_step_tpe2_kernel<8,4>"
     assert resets >= 64 * len(offsets)
     assert st["episodes"] >= n
 

@@ -318,3 +318,33 @@ def test_observation_function_integration_and_registries():
     with pytest.raises(ValueError, match="Unknown reward function 'invalid'"):
         get_reward_function(Invalid())
     env.close()
+
+
+def test_np_random_is_the_placement_generator_like_in_the_reference():
+    """gymnasium's env.np_random is the generator reset() places agents with: draws a caller makes between resets shift the
+    next placement.  The façade's generator lives on the device; env.np_random is a numpy view of its state that is pushed
+    back before the next unseeded reset — same numbers, same placements as the unmodified reference."""
+    from cases import readme_config
+    from oracle import refload
+
+    from collectivecrossing_b200 import CollectiveCrossingEnv
+
+    if not refload.available():
+        pytest.skip("reference neither mounted nor staged")
+    ref = refload.load()
+    cfg = readme_config()
+    ours, theirs = CollectiveCrossingEnv(cfg), ref.CollectiveCrossingEnv(refload.to_reference_config(cfg))
+    for env in (ours, theirs):
+        env.reset(seed=77)
+    a, b = ours.np_random.integers(0, 1000, size=5), theirs.np_random.integers(0, 1000, size=5)
+    assert np.array_equal(a, b)
+    assert ours.np_random.random() == theirs.np_random.random()
+    o1, _ = ours.reset()
+    o2, _ = theirs.reset()
+    assert o1.keys() == o2.keys() and all(np.array_equal(o1[k], o2[k]) for k in o1)
+    # and again without touching the generator in between
+    o1, _ = ours.reset()
+    o2, _ = theirs.reset()
+    assert all(np.array_equal(o1[k], o2[k]) for k in o1)
+    assert int(ours.np_random.integers(0, 10**6)) == int(theirs.np_random.integers(0, 10**6))
+    ours.close()
