@@ -517,7 +517,7 @@ def run_ours(args):
 
     # ---- e2e (headline): the reference's float32 rows in HOST buffers through the C ABI ----------------------------------
     launches_before_e2e = env.launch_count
-    host = env.make_host_buffers(pinned=True)
+    host = env.make_host_buffers(pinned=True, actions_out=False)   # the caller supplies the actions: they are not copied back
     e2e_ms = time_e2e(env, torch, dist, world, args.policy, args.e2e_steps, host)
     e2e = {"value": float(n) * A * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * A,
            "d2h_bytes_per_step": d2h_bytes(host, n, A), "steps": args.e2e_steps, "ms_per_step": e2e_ms,
@@ -533,7 +533,8 @@ def run_ours(args):
             e = BatchedCollectiveCrossing(cfg, n, dev, seed=2026, global_env_offset=rank * n, obs_dtype=obs or "none", auto_reset=True)
             e.set_host_expand(expand)
             e.reset()
-            h = e.make_host_buffers(pinned=True, n_steps=None if T_ == 1 else T_)
+            # (a caller that supplies the actions does not need them copied back)
+            h = e.make_host_buffers(pinned=True, n_steps=None if T_ == 1 else T_, actions_out=(T_ > 1 or on_device))
             ms_ = time_e2e(e, torch, dist, world, args.policy, max(args.e2e_steps, 2 * T_), h, T=T_, on_device_policy=on_device)
             pcie = d2h_bytes(h, n, A, T_, policy_roundtrip=(T_ == 1 and not on_device))
             if expand:

@@ -322,10 +322,11 @@ class BatchedCollectiveCrossing:
         return self.obs
 
     # ---- host-buffer path (what a numpy / RLlib caller binds) --------------------------------------
-    def make_host_buffers(self, pinned: bool = True, n_steps: int | None = None, obs: str | None = "same") -> dict:
+    def make_host_buffers(self, pinned: bool = True, n_steps: int | None = None, obs: str | None = "same", actions_out: bool = True) -> dict:
         """Host tensors for ``step_host`` (``n_steps=None``: per-step shapes) or ``rollout_host``
         (time-major ``[n_steps, ...]``).  ``obs``: "same" = the env's obs dtype, or "float32" / "int8" /
-        "table" / None for another delivery format of the same step."""
+        "table" / None for another delivery format of the same step.  ``actions_out=False``: the applied actions are not
+        copied back (a caller that supplies the actions has them)."""
         n, a = self.num_envs, self.num_agents
         lead = () if n_steps is None else (int(n_steps),)
         mk = lambda shape, dt: torch.zeros(lead + shape, dtype=dt, pin_memory=pinned)  # noqa: E731
@@ -340,7 +341,7 @@ class BatchedCollectiveCrossing:
             actions=mk((n, a), torch.int8), obs=obs_t,
             reward=mk((n, a), self.reward_torch_dtype), agent_flags=mk((n, a), torch.uint8),
             agent_info=None if self.agent_info is None else mk((n, a), torch.uint8),
-            env_flags=mk((n,), torch.uint8), actions_out=mk((n, a), torch.int8),
+            env_flags=mk((n,), torch.uint8), actions_out=mk((n, a), torch.int8) if actions_out else None,
         )
 
     def _host_io(self, host: dict, policy: Any, auto_reset: bool | None) -> _abi.CCStepIO:
@@ -348,7 +349,7 @@ class BatchedCollectiveCrossing:
         code = _policy_code(policy)
         io.actions = host["actions"].data_ptr() if code == 0 else None
         io.order = None
-        io.actions_out = host["actions_out"].data_ptr()
+        io.actions_out = None if host.get("actions_out") is None else host["actions_out"].data_ptr()
         obs = host["obs"]
         io.obs = None if obs is None else obs.data_ptr()
         io.reward = host["reward"].data_ptr()
