@@ -5,7 +5,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "cc_internal.h"
 #include "cc_kernel_tpe.cuh"   // KParams, layout constants (no kernel is instantiated in this file)
@@ -46,14 +49,27 @@ int cc_fail(int code, const char *fmt, ...) {
 
 int cc_cached_occupancy(cc_handle *h, const void *fn, int threads, int smem, int *per_sm) {
     for (const cc_launch_cfg &c : h->launch_cfgs)
-        if (c.fn == fn && c.smem == smem) { *per_sm = c.per_sm; return CC_OK; }
-    // the kernels also hold up to ~21 KB of static shared memory: always opt in to the dynamic size
-    // (once per instantiation and size: this is the cached path)
-    if (smem > 0) CC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (c.fn == fn && c.threads == threads && c.smem == smem) { *per_sm = c.per_sm; return CC_OK; }
+    // the kernels also hold up to ~21 KB of static shared memory: always opt in to the dynamic size.  The attribute belongs to
+    // the FUNCTION (per device), not to a handle, and one instantiation is launched with different sizes (4- and 2-warp CTAs,
+    // different handles): it is only ever raised.
+    {
+        static std::mutex mu;
+        static std::vector<std::pair<std::pair<const void *, int>, int>> raised;   // (function, device) -> largest size opted in to
+        std::lock_guard<std::mutex> lock(mu);
+        int *cur = nullptr;
+        for (auto &r : raised)
+            if (r.first.first == fn && r.first.second == h->device) cur = &r.second;
+        if (!cur) { raised.push_back({{fn, h->device}, 0}); cur = &raised.back().second; }
+        if (smem > *cur) {
+            CC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            *cur = smem;
+        }
+    }
     int n = 0;
     CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, threads, smem));
     if (n < 1) return cc_fail(CC_ERR_UNSUPPORTED, "kernel does not fit on an SM (%d bytes of dynamic shared memory)", smem);
-    h->launch_cfgs.push_back(cc_launch_cfg{fn, smem, n});
+    h->launch_cfgs.push_back(cc_launch_cfg{fn, threads, smem, n});
     *per_sm = n;
     return CC_OK;
 }

@@ -25,7 +25,7 @@ int cc_fail(int code, const char *fmt, ...);   // stores the thread-local messag
 // (cudaFuncSetAttribute + cudaOccupancyMaxActiveBlocksPerMultiprocessor cost more than a 65,536-env step)
 struct cc_launch_cfg {
     const void *fn;
-    int smem;
+    int threads, smem;
     int per_sm;
 };
 

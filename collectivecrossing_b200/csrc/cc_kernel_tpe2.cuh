@@ -29,7 +29,7 @@
 
 namespace ccb {
 
-constexpr int kT2Warps = 4;
+constexpr int kT2Warps = 4;            // warps per CTA (2 for batches that fit in one wave: finer CTAs balance the SMs better)
 constexpr int kT2Threads = kT2Warps * 32;
 constexpr int kT2MaxRows = 16, kT2MaxCols = 32, kT2MaxCells = 256;
 constexpr int kT2BitmapBytesPerWarp = kT2MaxRows * 128;   // row r of lane l at r * 128 + l * 4
@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
     // ---- once per CTA: the tables (L2-resident, 4.7 KB) and a clean bitmap ------------------------------------------
     for (int i = threadIdx.x; i < (int)(sizeof(T2Tables) / 16); i += blockDim.x)
         reinterpret_cast<uint4 *>(&tb)[i] = static_cast<const uint4 *>(p.t2_tables)[i];
-    for (int i = threadIdx.x; i < L::kDynBytes / 4; i += blockDim.x) reinterpret_cast<unsigned *>(smem)[i] = 0u;
+    const int n_warps = (int)blockDim.x >> 5;   // 4, or 2 for small batches (cc_launch_tpe.cu)
+    for (int i = threadIdx.x; i < n_warps * L::kBytesPerWarp / 4; i += blockDim.x) reinterpret_cast<unsigned *>(smem)[i] = 0u;
     __shared__ __align__(16) unsigned lut[L::kRows32 ? L::L1::kLutWords : 4];   // float32 rows: emission table of tpe_emit_group_tma
     if constexpr (L::kRows32) {
         __syncthreads();   // (the zero fill above must not overtake the constants below)
@@ -227,9 +228,9 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
     unsigned st_arrivals = 0;
     double st_rsum = 0.0;
     int errbits = 0;
-    const int total_warps = (int)gridDim.x * kT2Warps;
+    const int total_warps = (int)gridDim.x * n_warps;
     const int n_groups = (int)p.n_groups;
-    int gw = (int)blockIdx.x * kT2Warps + warp;
+    int gw = (int)blockIdx.x * n_warps + warp;
     int g_next = 0;
     for (; gw < n_groups; gw = g_next) {
         const int g = p.tpe_reverse ? n_groups - 1 - gw : gw;
@@ -599,11 +600,11 @@ __global__ void __launch_bounds__(kT2Threads, CCB_T2_MIN_BLOCKS) cc_step_tpe2_ke
         const unsigned long long *all = red_all;
         if (threadIdx.x >= 1 && threadIdx.x < 6) {
             unsigned long long v = 0;
-            for (int w = 0; w < kT2Warps; ++w) v += all[w * kStCount + threadIdx.x];
+            for (int w = 0; w < n_warps; ++w) v += all[w * kStCount + threadIdx.x];
             if (v) atomicAdd(&p.stats[threadIdx.x], v);
         } else if (threadIdx.x == 6 || threadIdx.x == 7) {
             double v = 0.0;
-            for (int w = 0; w < kT2Warps; ++w) v += __longlong_as_double((long long)all[w * kStCount + threadIdx.x]);
+            for (int w = 0; w < n_warps; ++w) v += __longlong_as_double((long long)all[w * kStCount + threadIdx.x]);
             if (v != 0.0) atomicAdd(reinterpret_cast<double *>(&p.stats[threadIdx.x]), v);
         } else if (threadIdx.x == 0 && blockIdx.x == 0) {
             atomicAdd(&p.stats[kStEnvSteps], (unsigned long long)p.n_envs * (unsigned long long)p.n_steps);

@@ -64,15 +64,23 @@ int launch_tpe2_t(cc_handle *h, KParams p, cudaStream_t s) {
     if (p.n_steps < 1) p.n_steps = 1;
     p.tpe_counter = h->tpe_counters + (h->tpe_launches & 1);
     p.tpe_counter_next = h->tpe_counters + ((h->tpe_launches + 1) & 1);
-    const int smem = L::kDynBytes;
+    // 4 warps per CTA; a batch that fits in one wave of those runs 2-warp CTAs: with about one group per warp the time is
+    // set by the SM that got the most CTAs, and finer CTAs spread 2,048 groups over 148 SMs as 14 / 13 instead of 16 / 12
+    int warps = ccb::kT2Warps;
     int per_sm = 0;
-    int rc = cc_cached_occupancy(h, reinterpret_cast<const void *>(kern), ccb::kT2Threads, smem, &per_sm);
+    int rc = cc_cached_occupancy(h, reinterpret_cast<const void *>(kern), warps * 32, warps * L::kBytesPerWarp, &per_sm);
     if (rc != CC_OK) return rc;
-    long long want = (p.n_groups + ccb::kT2Warps - 1) / ccb::kT2Warps;
+    if (p.n_groups <= (long long)h->sm_count * per_sm * warps) {
+        warps = 2;
+        rc = cc_cached_occupancy(h, reinterpret_cast<const void *>(kern), warps * 32, warps * L::kBytesPerWarp, &per_sm);
+        if (rc != CC_OK) return rc;
+    }
+    const int smem = warps * L::kBytesPerWarp;
+    long long want = (p.n_groups + warps - 1) / warps;
     long long cap = (long long)h->sm_count * per_sm;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, ccb::kT2Threads, smem, s>>>(p);
+    kern<<<grid, warps * 32, smem, s>>>(p);
     CC_CUDA(cudaGetLastError());
     snprintf(h->last_kernel, sizeof h->last_kernel, "ccb::cc_step_tpe2_kernel<%d,%d>", A, OBS);
     h->launches += 1;
