@@ -65,6 +65,7 @@ def config_dict(args, n_total):
                    f"every step's outputs written ([T, N, ...] buffers); steps % T as single-step launches"
                    if args.steps_per_launch > 1 else "cc_step: one launch per env-step"),
         "l2_policy": "inputs larger than L2 (no flush)" if args.envs >= 1 << 19 else "working set may fit L2",
+        "episode_phases": "step counters spread uniformly over [0, MaxSteps) after reset(): every step sees the steady-state share of episode ends",
         "parallelism": "independent env shards, one process per GPU, no data-path collective",
     }
 
@@ -334,6 +335,16 @@ def time_steps(env, torch, dist, args, steps, policy, world, per_launch=1, shard
     return ms, stats_t
 
 
+def desynchronise(env, torch):
+    """After reset() every env is at step 0, so all of them would hit MaxSteps in the same step, every 100 steps.  Spread the
+    episode phases (step counters uniform in [0, max_steps)): every step then sees the steady-state share of finished episodes."""
+    hi = int(env.cfg.max_steps)
+    if hi > 1:
+        g = torch.Generator(device=env.device)
+        g.manual_seed(1234 + env.global_env_offset)
+        env.step_count.copy_(torch.randint(0, hi, (env.num_envs,), generator=g, device=env.device, dtype=torch.int32))
+
+
 def median(vals):
     v = sorted(vals)
     return v[len(v) // 2] if len(v) % 2 else 0.5 * (v[len(v) // 2 - 1] + v[len(v) // 2])
@@ -449,6 +460,7 @@ def run_ours(args):
     env = sharded.env
     assert sharded.count == n and sharded.offset == rank * n
     env.reset()
+    desynchronise(env, torch)
     # steps per fused launch: at most --steps-per-launch, chosen so that the K timed steps are (almost) whole launches
     T = max(1, args.steps_per_launch)
     if T > 1:
@@ -533,6 +545,7 @@ def run_ours(args):
             e = BatchedCollectiveCrossing(cfg, n, dev, seed=2026, global_env_offset=rank * n, obs_dtype=obs or "none", auto_reset=True)
             e.set_host_expand(expand)
             e.reset()
+            desynchronise(e, torch)
             # (a caller that supplies the actions does not need them copied back)
             h = e.make_host_buffers(pinned=True, n_steps=None if T_ == 1 else T_, actions_out=(T_ > 1 or on_device))
             ms_ = time_e2e(e, torch, dist, world, args.policy, max(args.e2e_steps, 2 * T_), h, T=T_, on_device_policy=on_device)
@@ -597,6 +610,7 @@ def config5_sharded(args, torch, dist, cfg, world, rank, dev):
     sh = ShardedCollectiveCrossing(cfg, total, seed=5, device=dev, obs_dtype="float32", auto_reset=True)
     env = sh.env
     env.reset()
+    desynchronise(env, torch)
     for _ in range(30):
         env.step(policy="waiting")
     env.rollout_trajectory(T, policy="waiting")
@@ -653,9 +667,28 @@ def secondary(args, torch, dist, cfg):
         ("cfg3_64x32_64agents_simple_distance_all_1M_envs_int8_random", large_config(512), M, "int8", "random", "auto", 5, 1),
         ("cfg3_64x32_64agents_simple_distance_all_1M_envs_fp32_random", large_config(512), M, "float32", "random", "auto", 3, 1),
     )
+    # fused multi-step launches of the headline kernel at other lengths (first: before the 20-70 GB allocations of configs 3-5) (the state term 2(3A+4)+8 is paid once per T steps)
+    for T, n_envs in ((4, M), (16, M)):
+        env = BatchedCollectiveCrossing(cfg, n_envs, dev, seed=1, obs_dtype="float32", auto_reset=True)
+        env.reset()
+        desynchronise(env, torch)
+        env.rollout_trajectory(T, policy="greedy")
+        regions = [time_steps(env, torch, dist, args, 12 * T, "greedy", 1, T)[0] / (12 * T) for _ in range(3)]
+        ms = median(regions)
+        env.check_error()
+        a = env.num_agents
+        bytes_step = a + (2 * (3 * a + 4) + 8) / T + 5 * a + 1 + 4 * a * (6 + 4 * a)
+        out[f"fused_rollout_T{T}_1M_envs_fp32_greedy"] = {
+            "agent_steps_per_sec": n_envs * a / (ms * 1e-3), "ms_per_step": ms, "algorithmic_GBps": bytes_step * n_envs / (ms * 1e-3) / 1e9,
+            "frac": bytes_step * n_envs / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_env_step": bytes_step, "kernel": env.last_kernel_name,
+            "agents_per_env": a, "envs": n_envs, "steps_per_launch": T}
+        env.close()
+        del env
+        torch.cuda.empty_cache()
     for tag, c, n, obs, pol, kern, steps, T in runs:
         env = BatchedCollectiveCrossing(c, n, dev, seed=1, obs_dtype=obs, auto_reset=True, kernel=kern)
         env.reset()
+        desynchronise(env, torch)
         for _ in range(5):
             env.step(policy=pol)
         if T > 1:
@@ -674,23 +707,6 @@ def secondary(args, torch, dist, cfg):
         del env
         torch.cuda.empty_cache()
 
-    # fused multi-step launches of the headline kernel at other lengths (the state term 2(3A+4)+8 is paid once per T steps)
-    for T, n_envs in ((4, M), (16, M)):
-        env = BatchedCollectiveCrossing(cfg, n_envs, dev, seed=1, obs_dtype="float32", auto_reset=True)
-        env.reset()
-        env.rollout_trajectory(T, policy="greedy")
-        regions = [time_steps(env, torch, dist, args, 12 * T, "greedy", 1, T)[0] / (12 * T) for _ in range(3)]
-        ms = median(regions)
-        env.check_error()
-        a = env.num_agents
-        bytes_step = a + (2 * (3 * a + 4) + 8) / T + 5 * a + 1 + 4 * a * (6 + 4 * a)
-        out[f"fused_rollout_T{T}_1M_envs_fp32_greedy"] = {
-            "agent_steps_per_sec": n_envs * a / (ms * 1e-3), "ms_per_step": ms, "algorithmic_GBps": bytes_step * n_envs / (ms * 1e-3) / 1e9,
-            "frac": bytes_step * n_envs / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_env_step": bytes_step, "kernel": env.last_kernel_name,
-            "agents_per_env": a, "envs": n_envs, "steps_per_launch": T}
-        env.close()
-        del env
-        torch.cuda.empty_cache()
     return out
 
 
