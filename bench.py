@@ -584,7 +584,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8 lattice state, float64->float32 rewards", "data": "synthetic",
+            "dtype": "u8 (lattice cells, flag bytes; int32 step counters); rewards: f64 products rounded once to f32", "data": "synthetic",
             "config": config_dict(args, n * world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "gpu_launches_e2e": launches_e2e, "roofline": roofline, "cpu_baseline": cpu,
             "repetitions": {"count": reps, "ms_per_region": rep_ms, "value": "median", "spread": (max(rep_ms) - min(rep_ms)) / ms},

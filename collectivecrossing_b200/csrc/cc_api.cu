@@ -347,6 +347,8 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
         CC_CUDA(cudaStreamWaitEvent(h->s_k, h->ev_order, 0));
     }
     const uint64_t t0 = h->t;
+    // (a failure part-way leaves copies in flight that still write the caller's buffers: every exit drains the three streams)
+    auto enqueue_all = [&]() -> int {
     for (long long c = 0; c < n_chunks; ++c) {
         const int set = (int)(c % ring);
         const long long first = c * chunk, cnt = (N - first < chunk) ? N - first : chunk;
@@ -371,7 +373,7 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
         }
         if (reuse) CC_CUDA(cudaStreamWaitEvent(h->s_k, h->ev_out[set], 0));      // this set's previous outputs have left
         rc = rollout_on(h, &d, h->s_k, T, first, cnt, cnt, t0);
-        if (rc != CC_OK) { cudaStreamSynchronize(h->s_out); cudaStreamSynchronize(h->s_k); return rc; }
+        if (rc != CC_OK) return rc;
         CC_CUDA(cudaEventRecord(h->ev_k[set], h->s_k));
         CC_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_k[set], 0));
         // the biggest output first, the per-env flags last
@@ -387,6 +389,13 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
         rc = copy_slices(io->env_flags, d.env_flags, 1, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc;
         CC_CUDA(cudaEventRecord(h->ev_out[set], h->s_out));
     }
+    return CC_OK;
+    };
+    rc = enqueue_all();
+    if (rc != CC_OK) {
+        cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_k); cudaStreamSynchronize(h->s_out);
+        return rc;
+    }
     h->t = t0 + (uint64_t)T;
     if (expand) {   // rebuild the rows of every chunk as soon as its table has arrived (later chunks are still in flight)
         const size_t row_b = obs_env_bytes(A, io->obs_dtype);
@@ -397,7 +406,7 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
                 const size_t e0 = (size_t)t * N + (size_t)first;
                 rc = cc_expand_obs_host(&h->cfg, cnt, static_cast<const int8_t *>(h->host_table) + e0 * obs_b,
                                         static_cast<char *>(io->obs) + e0 * row_b, io->obs_dtype, h->host_expand < 0 ? 0 : h->host_expand);
-                if (rc != CC_OK) return rc;
+                if (rc != CC_OK) { cudaStreamSynchronize(h->s_out); return rc; }
             }
         }
     }
