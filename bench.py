@@ -425,11 +425,6 @@ def time_e2e(env, torch, dist, world, policy, steps, host, T=1, on_device_policy
     return ms / (calls * T)
 
 
-def d2h_bytes(host, n, A, T=1, policy_roundtrip=True):
-    total = sum(v.numel() * v.element_size() for k, v in host.items() if v is not None and k != "actions") // T
-    return total + (n * A if policy_roundtrip else 0)
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -528,43 +523,49 @@ def run_ours(args):
                 "formula": "12A+17+s_obs*A*(6+4A), A=8 (SURVEY.md 8d); in a fused launch of T steps the state term 2(3A+4)+8 is paid once per T steps"}
 
     # ---- e2e (headline): the reference's float32 rows in HOST buffers through the C ABI ----------------------------------
+    # (the handle's own choice of row delivery: on a host with >= 8 threads the [A,4] table crosses PCIe and the float32 rows are
+    #  rebuilt in the caller's buffer by the library's host threads; d2h_bytes_per_step is what the library copied)
     launches_before_e2e = env.launch_count
     host = env.make_host_buffers(pinned=True, actions_out=False)   # the caller supplies the actions: they are not copied back
     e2e_ms = time_e2e(env, torch, dist, world, args.policy, args.e2e_steps, host)
-    e2e = {"value": float(n) * A * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * A,
-           "d2h_bytes_per_step": d2h_bytes(host, n, A), "steps": args.e2e_steps, "ms_per_step": e2e_ms,
-           "path": "cc_policy_actions -> D2H actions (pinned) -> cc_step_host(H2D actions | fused step kernel | D2H obs/reward/flags, "
-                   "chunks of envs pipelined over three streams); observations are the reference's float32 rows"}
+    call = env.last_host_call()
+    rows_bytes = host["obs"].numel() * host["obs"].element_size()
+    e2e = {"value": float(n) * A * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": call["h2d_bytes"],
+           "d2h_bytes_per_step": call["d2h_bytes"] + n * A, "steps": args.e2e_steps, "ms_per_step": e2e_ms,
+           "host_rows_bytes_per_step": rows_bytes, "expand_threads": call["expand_threads"], "chunks": call["chunks"],
+           "path": "cc_policy_actions -> D2H actions (pinned) -> cc_step_host(H2D actions | fused step kernel | D2H "
+                   + ("observation TABLE/reward/flags | float32 rows rebuilt in the caller's buffer by %d host threads (cc_set_host_expand, automatic)" % call["expand_threads"]
+                      if call["expand_threads"] else "obs rows/reward/flags")
+                   + ", chunks of envs pipelined over three streams); the caller receives the reference's float32 rows"}
     launches_e2e = env.launch_count - launches_before_e2e
     del host
 
     # ---- the same path with the other delivery formats of the SAME step (labelled, never the headline) ----------------------
     e2e_modes = {}
     if not args.no_extras:
-        def mode(tag, obs, expand=0, T_=1, on_device=False, note=""):
+        def mode(tag, obs, expand=None, T_=1, on_device=False, note=""):
             e = BatchedCollectiveCrossing(cfg, n, dev, seed=2026, global_env_offset=rank * n, obs_dtype=obs or "none", auto_reset=True)
-            e.set_host_expand(expand)
+            e.set_host_expand(expand if expand is not None else (sharded.host_threads or -2))
             e.reset()
             desynchronise(e, torch)
             # (a caller that supplies the actions does not need them copied back)
             h = e.make_host_buffers(pinned=True, n_steps=None if T_ == 1 else T_, actions_out=(T_ > 1 or on_device))
             ms_ = time_e2e(e, torch, dist, world, args.policy, max(args.e2e_steps, 2 * T_), h, T=T_, on_device_policy=on_device)
-            pcie = d2h_bytes(h, n, A, T_, policy_roundtrip=(T_ == 1 and not on_device))
-            if expand:
-                pcie -= h["obs"].numel() * h["obs"].element_size() // T_ - n * A * 4   # the table crosses PCIe, not the rows
-            e2e_modes[tag] = {"agent_steps_per_sec": float(n) * A * world / (ms_ * 1e-3), "ms_per_step": ms_, "d2h_bytes_per_step": pcie,
-                              "vs_float32_rows": e2e_ms / ms_, "note": note}
+            c_ = e.last_host_call()
+            e2e_modes[tag] = {"agent_steps_per_sec": float(n) * A * world / (ms_ * 1e-3), "ms_per_step": ms_,
+                              "d2h_bytes_per_step": c_["d2h_bytes"] // T_ + (n * A if (T_ == 1 and not on_device) else 0),
+                              "expand_threads": c_["expand_threads"], "vs_headline_e2e": e2e_ms / ms_, "note": note}
             e.close()
             del e, h
             torch.cuda.empty_cache()
 
+        mode("float32_rows_over_pcie", "float32", expand=0, note="cc_set_host_expand(0): the float32 rows cross PCIe as the kernel wrote them (round 1's path, pipelined)")
         mode("table", "table", note="obs = compact table int8 [N,A,4] (CC_OBS_TABLE); rows on demand through cc_expand_obs_host")
         if world == 1:
-            mode("int8_rows", "int8", note="obs = the reference's rows as int8")
+            mode("int8_rows", "int8", note="obs = the reference's rows as int8 (they cross PCIe)")
             mode("table_policy_on_device", "table", on_device=True, note="cc_step_host with the greedy policy in the kernel: no action round trip")
             mode("rollout_host_T8_table", "table", T_=8, note="cc_rollout_host: 8 steps per call, chunks stream out while the next chunk runs")
-            mode("float32_rows_rebuilt_on_host", "float32", expand=-1,
-                 note="cc_set_host_expand(-1): the table crosses PCIe, the float32 rows are rebuilt in the caller's buffer by all host threads")
+            mode("rollout_host_T8_float32", "float32", T_=8, note="cc_rollout_host: 8 steps per call, float32 rows")
 
     extras = {}
     if not args.no_extras:

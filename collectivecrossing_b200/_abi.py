@@ -102,6 +102,7 @@ EXPORTS = {
     "cc_set_kernel_variant": (C.c_int, [_P, _I32]),
     "cc_last_kernel_variant": (_I32, [_P]),
     "cc_last_kernel_name": (C.c_char_p, [_P]),
+    "cc_last_host_call": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "cc_timing_begin": (C.c_int, [_P, _P]),
     "cc_timing_end": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
     "cc_last_error": (C.c_char_p, []),

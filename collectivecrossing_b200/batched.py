@@ -387,13 +387,21 @@ class BatchedCollectiveCrossing:
         _native.check(self._lib.cc_rollout_host(self._h, C.byref(io), int(n_steps)))
         return host
 
+    def last_host_call(self) -> dict:
+        """What the last ``step_host`` / ``rollout_host`` did (``cc_last_host_call``): chunks, envs per chunk, host threads that
+        rebuilt rows (0: rows crossed PCIe), bytes copied in each direction."""
+        out = (C.c_int64 * 5)()
+        _native.check(self._lib.cc_last_host_call(self._h, out))
+        return dict(zip(("chunks", "chunk_envs", "expand_threads", "h2d_bytes", "d2h_bytes"), (int(v) for v in out)))
+
     def set_host_chunk(self, chunk_envs: int) -> None:
         """Envs per chunk of the host pipeline (0 = automatic)."""
         _native.check(self._lib.cc_set_host_chunk(self._h, int(chunk_envs)))
 
     def set_host_expand(self, n_threads: int) -> None:
-        """Rows of the host path rebuilt on the host from the compact table (``n_threads`` host threads, -1 = all,
-        0 = off: rows cross PCIe as the kernel wrote them).  Same bytes either way."""
+        """Rows of the host path rebuilt on the host from the compact table: ``n_threads`` host threads, -1 = all,
+        0 = off (rows cross PCIe as the kernel wrote them), -2 = automatic (the default of a new env: all threads when
+        the host has at least 8 and a call delivers at least 16 MiB of rows).  Same bytes either way."""
         _native.check(self._lib.cc_set_host_expand(self._h, int(n_threads)))
 
     def expand_table_host(self, table: torch.Tensor, out: torch.Tensor | None = None, dtype: torch.dtype = torch.float32,

@@ -1,6 +1,8 @@
 // cc_api.cu — the extern "C" boundary declared in include/ccb200.h.
 // Host-side plumbing only: handle, kernel dispatch, host<->device staging, statistics.  The kernels are
 // instantiated in cc_launch_lanes.cu / cc_launch_tpe.cu; the host-side row expansion is cc_expand.cpp.
+#include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -11,6 +13,7 @@
 #include <vector>
 
 #include "cc_internal.h"
+#include "cc_workers.h"
 #include "cc_kernel_tpe.cuh"   // KParams, layout constants (no kernel is instantiated in this file)
 
 #ifndef CCB_TPE_ALTERNATE
@@ -272,6 +275,8 @@ int ensure_host_path(cc_handle *h, size_t bytes) {
 }
 
 // rows of `row_bytes` bytes: device [T][c] (compact) <-> host [T][N], the chunk starting at env `first`
+thread_local int64_t *g_copy_bytes = nullptr;   // host_pipeline's {h2d, d2h} byte counters of the call in progress
+
 int copy_slices(void *dst, const void *src, size_t row_bytes, int T, long long c, long long N, long long first, bool to_device, cudaStream_t s) {
     if (T > 1 && (size_t)N * row_bytes >= (size_t)1 << 31) {   // pitch beyond what 2D copies accept: slice by slice
         for (int t = 0; t < T; ++t) {
@@ -282,6 +287,7 @@ int copy_slices(void *dst, const void *src, size_t row_bytes, int T, long long c
         }
         return CC_OK;
     }
+    if (g_copy_bytes) g_copy_bytes[to_device ? 0 : 1] += (int64_t)((size_t)T * (size_t)c * row_bytes);
     if (to_device) {
         const char *hsrc = static_cast<const char *>(src) + (size_t)first * row_bytes;
         if (T == 1) CC_CUDA(cudaMemcpyAsync(dst, hsrc, (size_t)c * row_bytes, cudaMemcpyHostToDevice, s));
@@ -303,7 +309,13 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
     const int A = h->A;
     const long long N = h->n_envs;
     // rows rebuilt on the host (cc_set_host_expand): the kernel writes the table, the table crosses PCIe
-    const bool expand = h->host_expand != 0 && is_rows(io->obs_dtype);
+    bool expand = false;
+    int expand_threads = 0;   // 0 = every hardware thread
+    if (is_rows(io->obs_dtype) && h->host_expand != CC_HOST_EXPAND_OFF) {
+        if (h->host_expand == CC_HOST_EXPAND_AUTO)   // (int8 rows: 16 threads rebuild ~43 GB/s, PCIe delivers ~54: they keep crossing PCIe)
+            expand = io->obs_dtype == CC_OBS_FP32 && std::thread::hardware_concurrency() >= 8 && (size_t)T * (size_t)N * obs_env_bytes(A, io->obs_dtype) >= ((size_t)16 << 20);
+        else { expand = true; expand_threads = h->host_expand > 0 ? h->host_expand : 0; }
+    }
     const int k_obs = expand ? CC_OBS_TABLE : io->obs_dtype;
     const size_t obs_b = obs_env_bytes(A, k_obs), rew_b = (size_t)A * (size_t)io->reward_dtype;
     const size_t per_env_step = obs_b + rew_b + 5 * (size_t)A + 1;
@@ -346,6 +358,11 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
         CC_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_order, 0));
         CC_CUDA(cudaStreamWaitEvent(h->s_k, h->ev_order, 0));
     }
+    h->last_host[0] = n_chunks; h->last_host[1] = chunk; h->last_host[2] = 0; h->last_host[3] = h->last_host[4] = 0;
+    struct CountCopies {
+        explicit CountCopies(int64_t *c) { g_copy_bytes = c; }
+        ~CountCopies() { g_copy_bytes = nullptr; }
+    } count_copies(h->last_host + 3);
     const uint64_t t0 = h->t;
     // (a failure part-way leaves copies in flight that still write the caller's buffers: every exit drains the three streams)
     auto enqueue_all = [&]() -> int {
@@ -399,15 +416,29 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
     h->t = t0 + (uint64_t)T;
     if (expand) {   // rebuild the rows of every chunk as soon as its table has arrived (later chunks are still in flight)
         const size_t row_b = obs_env_bytes(A, io->obs_dtype);
-        for (long long c = 0; c < n_chunks; ++c) {
-            const long long first = c * chunk, cnt = (N - first < chunk) ? N - first : chunk;
-            CC_CUDA(cudaEventSynchronize(h->ev_chunk[c]));
-            for (int t = 0; t < T; ++t) {
-                const size_t e0 = (size_t)t * N + (size_t)first;
-                rc = cc_expand_obs_host(&h->cfg, cnt, static_cast<const int8_t *>(h->host_table) + e0 * obs_b,
-                                        static_cast<char *>(io->obs) + e0 * row_b, io->obs_dtype, h->host_expand < 0 ? 0 : h->host_expand);
-                if (rc != CC_OK) { cudaStreamSynchronize(h->s_out); return rc; }
+        const int crew = cc_expand_thread_count(expand_threads, chunk);
+        h->last_host[2] = crew;
+        if (!h->workers) h->workers = new cc_worker_pool();
+        std::atomic<int> cuda_err{(int)cudaSuccess};
+        // every thread waits for the chunk's event itself and expands its own slice of the chunk: no hand-over between threads
+        h->workers->run(crew, [&](int w) {
+            cudaSetDevice(h->device);
+            for (long long c = 0; c < n_chunks; ++c) {
+                const long long first = c * chunk, cnt = (N - first < chunk) ? N - first : chunk;
+                const cudaError_t e = cudaEventSynchronize(h->ev_chunk[c]);
+                if (e != cudaSuccess) { cuda_err.store((int)e); return; }
+                const long long per = (cnt + crew - 1) / crew;
+                const long long a = std::min<long long>(cnt, (long long)w * per), b = std::min<long long>(cnt, (long long)(w + 1) * per);
+                for (int t = 0; t < T; ++t) {
+                    const size_t e0 = (size_t)t * N + (size_t)first;
+                    cc_expand_rows_range(&h->cfg, a, b, static_cast<const int8_t *>(h->host_table) + e0 * obs_b,
+                                         static_cast<char *>(io->obs) + e0 * row_b, io->obs_dtype);
+                }
             }
+        });
+        if (cuda_err.load() != (int)cudaSuccess) {
+            cudaStreamSynchronize(h->s_out);
+            return cc_fail(CC_ERR_CUDA, "cudaEventSynchronize(chunk): %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
         }
     }
     CC_CUDA(cudaStreamSynchronize(h->s_out));
@@ -492,6 +523,7 @@ void cc_destroy(cc_handle *h) {
     cudaDeviceSynchronize();
     if (h->own_block) cudaFree(h->own_block);
     if (h->stage_block) cudaFree(h->stage_block);
+    delete h->workers;
     if (h->host_table) cudaFreeHost(h->host_table);
     for (cudaEvent_t ev : h->ev_chunk) cudaEventDestroy(ev);
     if (h->gen) cudaFree(h->gen);
@@ -596,6 +628,7 @@ int cc_step_host(cc_handle *h, const cc_step_io *io) { return host_pipeline(h, i
 int cc_rollout_host(cc_handle *h, const cc_step_io *io, int32_t n_steps) { return host_pipeline(h, io, n_steps); }
 int cc_set_host_expand(cc_handle *h, int32_t n_threads) {
     if (!h) return cc_fail(CC_ERR_INVALID_ARG, "null handle");
+    if (n_threads < CC_HOST_EXPAND_AUTO) return cc_fail(CC_ERR_INVALID_ARG, "cc_set_host_expand: n_threads must be >= 0, CC_HOST_EXPAND_ALL or CC_HOST_EXPAND_AUTO, got %d", n_threads);
     h->host_expand = n_threads;
     return CC_OK;
 }
@@ -724,6 +757,11 @@ int cc_set_kernel_variant(cc_handle *h, int32_t variant) {
 }
 int32_t cc_last_kernel_variant(const cc_handle *h) { return h ? h->last_variant : 0; }
 const char *cc_last_kernel_name(const cc_handle *h) { return h ? h->last_kernel : ""; }
+int cc_last_host_call(const cc_handle *h, int64_t out[5]) {
+    if (!h || !out) return cc_fail(CC_ERR_INVALID_ARG, "cc_last_host_call: null pointer");
+    for (int k = 0; k < 5; ++k) out[k] = h->last_host[k];
+    return CC_OK;
+}
 
 int cc_timing_begin(cc_handle *h, void *stream) {
     if (!h) return cc_fail(CC_ERR_INVALID_ARG, "null handle");

@@ -8,8 +8,11 @@
 // memory: pure data movement, no env logic, no CUDA.  The rows it writes are bit-identical to what the step kernels
 // write for CC_OBS_INT8 / CC_OBS_FP32 (tests/test_gpu_host_path.py).
 //
-// Output is written with non-temporal 16-byte stores where the ISA has them (SSE2: every x86-64): the rows are
-// written once and read by someone else, so read-for-ownership traffic would double the DRAM bytes.
+// How a thread works: per env it converts the table once into a row TEMPLATE [0, 0, head, B_0 .. B_(A-1)]; a row is
+// one copy of the template plus six patched values (own position, own block = -1).  Rows are assembled in a staging
+// buffer whose offsets are congruent to the destination addresses modulo 64 and leave as whole cache lines through
+// non-temporal stores (SSE2: every x86-64; 32-byte stores where the CPU has AVX2): the rows are written once and read
+// by someone else, so read-for-ownership traffic would double the DRAM bytes.
 #include <stdint.h>
 #include <string.h>
 
@@ -19,83 +22,142 @@
 
 #include "../../include/ccb200.h"
 
-#if defined(__SSE2__)
-#include <emmintrin.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define CCB_X86 1
+#else
+#define CCB_X86 0
 #endif
 
 int cc_fail(int code, const char *fmt, ...);
 
 namespace {
 
-// Sequential writer of one thread's contiguous output range: small pieces are appended to an aligned local buffer
-// that is flushed with streaming stores.
-class StreamWriter {
-  public:
-    explicit StreamWriter(unsigned char *dst) : dst_(dst), fill_(0) {
-        // bytes in front of the first 16-byte boundary go out directly
-        head_ = (size_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+constexpr size_t kMaxRowBytes = (size_t)(6 + 4 * CC_MAX_AGENTS) * sizeof(float);
+
+#if CCB_X86
+void stream_lines_sse2(unsigned char *dst, const unsigned char *src, size_t n) {   // n: multiple of 64; both 64-byte aligned
+    for (size_t o = 0; o < n; o += 64) {
+        const __m128i a = _mm_load_si128(reinterpret_cast<const __m128i *>(src + o)), b = _mm_load_si128(reinterpret_cast<const __m128i *>(src + o + 16)),
+                      c = _mm_load_si128(reinterpret_cast<const __m128i *>(src + o + 32)), d = _mm_load_si128(reinterpret_cast<const __m128i *>(src + o + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o), a);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o + 48), d);
     }
-    void push(const void *src, size_t n) {
-        const unsigned char *s = static_cast<const unsigned char *>(src);
-        while (head_ && n) { *dst_++ = *s++; --head_; --n; }
-        while (n) {
-            const size_t k = std::min(n, kBuf - fill_);
-            memcpy(buf_ + fill_, s, k);
-            fill_ += k; s += k; n -= k;
-            if (fill_ == kBuf) flush_full();
-        }
+}
+__attribute__((target("avx2"))) void stream_lines_avx2(unsigned char *dst, const unsigned char *src, size_t n) {
+    for (size_t o = 0; o < n; o += 64) {
+        const __m256i a = _mm256_load_si256(reinterpret_cast<const __m256i *>(src + o)), b = _mm256_load_si256(reinterpret_cast<const __m256i *>(src + o + 32));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + o), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + o + 32), b);
     }
-    void finish() {
-        const size_t whole = fill_ & ~(size_t)15;
-        stream(whole);
-        memcpy(dst_, buf_ + whole, fill_ - whole);
-        dst_ += fill_ - whole;
-        fill_ = 0;
-#if defined(__SSE2__)
-        _mm_sfence();
+}
+using StreamFn = void (*)(unsigned char *, const unsigned char *, size_t);
+StreamFn pick_stream() { return __builtin_cpu_supports("avx2") ? stream_lines_avx2 : stream_lines_sse2; }
+const StreamFn g_stream = pick_stream();
 #endif
+
+// Sequential writer of one thread's contiguous output range.  buf_[o] stands for the byte at base_ + o, base_ is
+// 64-byte aligned: whole cache lines are drained with streaming stores, the ragged first and last bytes with memcpy.
+class LineWriter {
+  public:
+    explicit LineWriter(unsigned char *dst) {
+        lo_ = fill_ = (size_t)(reinterpret_cast<uintptr_t>(dst) & 63);
+        base_ = dst - lo_;
     }
+    unsigned char *cursor() { return buf_ + fill_; }          // room for one row of any crew
+    void advance(size_t n) {
+        fill_ += n;
+        if (fill_ >= kDrain) drain(false);
+    }
+    void finish() { drain(true); }
 
   private:
-    static constexpr size_t kBuf = 8192;
-    void stream(size_t n) {   // n is a multiple of 16, dst_ is 16-byte aligned
-#if defined(__SSE2__)
-        for (size_t o = 0; o < n; o += 16)
-            _mm_stream_si128(reinterpret_cast<__m128i *>(dst_ + o), _mm_load_si128(reinterpret_cast<const __m128i *>(buf_ + o)));
+    static constexpr size_t kDrain = 16384;
+    void drain(bool last) {
+        size_t o = lo_;
+        if (o & 63) {   // the bytes in front of the first cache-line boundary
+            const size_t k = std::min(fill_, (o + 63) & ~(size_t)63) - o;
+            memcpy(base_ + o, buf_ + o, k);
+            o += k;
+        }
+        const size_t lines = (fill_ - o) & ~(size_t)63;
+#if CCB_X86
+        g_stream(base_ + o, buf_ + o, lines);
 #else
-        memcpy(dst_, buf_, n);
+        memcpy(base_ + o, buf_ + o, lines);
 #endif
-        dst_ += n;
+        o += lines;
+        if (last) {
+            memcpy(base_ + o, buf_ + o, fill_ - o);
+#if CCB_X86
+            _mm_sfence();
+#endif
+            lo_ = fill_;
+            return;
+        }
+        const size_t rest = fill_ - o;   // < 64: the open cache line moves to the front
+        memcpy(buf_, buf_ + o, rest);
+        base_ += o;
+        lo_ = 0;
+        fill_ = rest;
     }
-    void flush_full() { stream(kBuf); fill_ = 0; }
-    alignas(64) unsigned char buf_[kBuf];
-    unsigned char *dst_;
-    size_t fill_, head_;
+    alignas(64) unsigned char buf_[kDrain + kMaxRowBytes + 64];
+    unsigned char *base_;
+    size_t lo_, fill_;
 };
 
-template <typename T>
+// AC: the crew size when it is a compile-time constant (the row copies become straight-line vector moves), 0 otherwise
+template <typename T, int AC>
 void expand_range(const cc_config *cfg, int64_t e0, int64_t e1, const int8_t *table, T *obs) {
-    const int A = cfg->num_boarding + cfg->num_exiting, L = 6 + 4 * A;
+    const int A = AC ? AC : cfg->num_boarding + cfg->num_exiting, L = 6 + 4 * A;
+    const size_t row_bytes = (size_t)L * sizeof(T);
+    alignas(64) T tmpl[6 + 4 * CC_MAX_AGENTS];
     // observations.py:66-75: door centre, division, door boundaries (per-config constants)
-    const T head[4] = {(T)((cfg->door_left + cfg->door_right) / 2), (T)cfg->division_y, (T)cfg->door_left, (T)cfg->door_right};
+    tmpl[0] = tmpl[1] = (T)0;
+    tmpl[2] = (T)((cfg->door_left + cfg->door_right) / 2); tmpl[3] = (T)cfg->division_y; tmpl[4] = (T)cfg->door_left; tmpl[5] = (T)cfg->door_right;
     const T masked[4] = {(T)-1, (T)-1, (T)-1, (T)-1};
-    T blocks[4 * CC_MAX_AGENTS];
-    StreamWriter w(reinterpret_cast<unsigned char *>(obs + e0 * (int64_t)A * L));
+    LineWriter w(reinterpret_cast<unsigned char *>(obs + e0 * (int64_t)A * L));
     for (int64_t e = e0; e < e1; ++e) {
         const int8_t *t = table + e * 4 * (int64_t)A;
-        for (int k = 0; k < 4 * A; ++k) blocks[k] = (T)t[k];
+        for (int k = 0; k < 4 * A; ++k) tmpl[6 + k] = (T)t[k];
         for (int i = 0; i < A; ++i) {
-            w.push(blocks + 4 * i, 2 * sizeof(T));                 // own position (observations.py:62-64)
-            w.push(head, sizeof head);
-            if (i) w.push(blocks, (size_t)(4 * i) * sizeof(T));    // agents before i
-            w.push(masked, sizeof masked);                         // the own block (observations.py:92-93)
-            if (i + 1 < A) w.push(blocks + 4 * (i + 1), (size_t)(4 * (A - 1 - i)) * sizeof(T));
+            unsigned char *p = w.cursor();
+            memcpy(p, tmpl, row_bytes);
+            memcpy(p, tmpl + 6 + 4 * i, 2 * sizeof(T));                       // own position (observations.py:62-64)
+            memcpy(p + (size_t)(6 + 4 * i) * sizeof(T), masked, sizeof masked);   // the own block (observations.py:92-93)
+            w.advance(row_bytes);
         }
     }
     w.finish();
 }
 
+template <typename T>
+void expand_any(const cc_config *cfg, int64_t e0, int64_t e1, const int8_t *table, T *obs) {
+    switch (cfg->num_boarding + cfg->num_exiting) {
+        case 8: return expand_range<T, 8>(cfg, e0, e1, table, obs);      // the README crew (BASELINE configs 1, 2, 4, 5)
+        case 64: return expand_range<T, 64>(cfg, e0, e1, table, obs);    // BASELINE config 3
+        default: return expand_range<T, 0>(cfg, e0, e1, table, obs);
+    }
+}
+
 }  // namespace
+
+// One thread's share (internal; cc_api.cu's host pipeline runs it on its own workers).
+void cc_expand_rows_range(const cc_config *cfg, int64_t e0, int64_t e1, const int8_t *table, void *obs, int32_t obs_dtype) {
+    if (e0 >= e1) return;
+    if (obs_dtype == CC_OBS_FP32) expand_any<float>(cfg, e0, e1, table, static_cast<float *>(obs));
+    else expand_any<int8_t>(cfg, e0, e1, table, static_cast<int8_t *>(obs));
+}
+
+// How many threads a job of n_envs gets when the caller asked for `requested` (<= 0: all the host has).
+int cc_expand_thread_count(int32_t requested, int64_t n_envs) {
+    int threads = requested > 0 ? requested : (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    const int64_t min_per_thread = 2048;   // below this a thread's start-up costs more than its share
+    return (int)std::max<int64_t>(1, std::min<int64_t>(threads, (n_envs + min_per_thread - 1) / min_per_thread));
+}
 
 extern "C" int cc_expand_obs_host(const cc_config *cfg, int64_t n_envs, const int8_t *table, void *obs, int32_t obs_dtype, int32_t n_threads) {
     if (!cfg || !table || !obs) return cc_fail(CC_ERR_INVALID_ARG, "cc_expand_obs_host: null pointer");
@@ -103,23 +165,16 @@ extern "C" int cc_expand_obs_host(const cc_config *cfg, int64_t n_envs, const in
     if (A < 1 || A > CC_MAX_AGENTS) return cc_fail(CC_ERR_UNSUPPORTED, "agents per env must be in 1..%d, got %d", CC_MAX_AGENTS, A);
     if (obs_dtype != CC_OBS_INT8 && obs_dtype != CC_OBS_FP32) return cc_fail(CC_ERR_INVALID_ARG, "cc_expand_obs_host writes CC_OBS_INT8 or CC_OBS_FP32 rows");
     if (n_envs <= 0) return CC_OK;
-    int threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-    if (threads < 1) threads = 1;
-    const int64_t min_per_thread = 2048;   // below this a thread's start-up costs more than its share
-    threads = (int)std::min<int64_t>(threads, (n_envs + min_per_thread - 1) / min_per_thread);
-    auto run = [&](int64_t e0, int64_t e1) {
-        if (obs_dtype == CC_OBS_FP32) expand_range<float>(cfg, e0, e1, table, static_cast<float *>(obs));
-        else expand_range<int8_t>(cfg, e0, e1, table, static_cast<int8_t *>(obs));
-    };
-    if (threads <= 1) { run(0, n_envs); return CC_OK; }
+    const int threads = cc_expand_thread_count(n_threads, n_envs);
+    if (threads <= 1) { cc_expand_rows_range(cfg, 0, n_envs, table, obs, obs_dtype); return CC_OK; }
     std::vector<std::thread> pool;
     pool.reserve(threads - 1);
     const int64_t per = (n_envs + threads - 1) / threads;
     for (int k = 1; k < threads; ++k) {
         const int64_t e0 = std::min<int64_t>(n_envs, k * per), e1 = std::min<int64_t>(n_envs, (k + 1) * per);
-        if (e0 < e1) pool.emplace_back(run, e0, e1);
+        if (e0 < e1) pool.emplace_back(cc_expand_rows_range, cfg, e0, e1, table, obs, obs_dtype);
     }
-    run(0, std::min<int64_t>(n_envs, per));
+    cc_expand_rows_range(cfg, 0, std::min<int64_t>(n_envs, per), table, obs, obs_dtype);
     for (auto &th : pool) th.join();
     return CC_OK;
 }

@@ -9,6 +9,7 @@
 
 #include "../../include/ccb200.h"
 
+class cc_worker_pool;   // cc_workers.h
 namespace ccb {
 struct KParams;
 struct Pcg64State;
@@ -66,12 +67,18 @@ struct cc_handle {
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[kRing] = {}, ev_k[kRing] = {}, ev_out[kRing] = {};
     int64_t host_chunk = 0;   // cc_set_host_chunk (0 = automatic)
-    int host_expand = 0;      // cc_set_host_expand: threads that rebuild observation rows on the host (0 = rows cross PCIe)
+    int host_expand = CC_HOST_EXPAND_AUTO;   // cc_set_host_expand: threads that rebuild observation rows on the host (0 = rows cross PCIe)
     void *host_table = nullptr;          // pinned scratch of the tables the host expands
     size_t host_table_bytes = 0;
     std::vector<cudaEvent_t> ev_chunk;   // one event per chunk: its outputs are complete in host memory
+    int64_t last_host[5] = {};           // cc_last_host_call: chunks, envs per chunk, expanding threads, H2D bytes, D2H bytes
+    cc_worker_pool *workers = nullptr;   // the threads that expand (created by the first call that needs them)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // cc_timing_*
 };
+
+// cc_expand.cpp: rows of envs [e0, e1) of `table` into `obs` on the calling thread; threads a job of n_envs is worth
+void cc_expand_rows_range(const cc_config *cfg, int64_t e0, int64_t e1, const int8_t *table, void *obs, int32_t obs_dtype);
+int cc_expand_thread_count(int32_t requested, int64_t n_envs);
 
 // `per_sm` resident CTAs of kernel `fn` with `threads` threads and `smem` bytes of dynamic shared memory (cached);
 // opts the kernel in to `smem` when it exceeds what the default limit leaves beside the static tables

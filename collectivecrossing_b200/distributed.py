@@ -61,6 +61,17 @@ def derived_stats(stats: dict) -> dict:
     }
 
 
+def host_threads_per_rank() -> int:
+    """Host threads one rank may use for the host-buffer path when several ranks share a node (torchrun sets
+    LOCAL_WORLD_SIZE); 0 = alone on the node, keep the library's automatic choice."""
+    import os
+
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    if local_world <= 1:
+        return 0
+    return max(2, (os.cpu_count() or 1) // local_world)
+
+
 class ShardedCollectiveCrossing:
     """``total_envs`` envs split over the ranks of the default process group.
 
@@ -91,6 +102,10 @@ class ShardedCollectiveCrossing:
             env_factory = lambda cfg, n, **kw: BatchedCollectiveCrossing(cfg, n, device, **kw)  # noqa: E731
         self.device = device
         self.env = env_factory(config, self.count, global_env_offset=self.offset, seed=seed, **env_kwargs)
+        self.host_threads = host_threads_per_rank()
+        if self.host_threads and hasattr(self.env, "set_host_expand"):
+            # the ranks of a node share its cores AND its PCIe / memory paths: each rebuilds its rows with its share of the threads
+            self.env.set_host_expand(self.host_threads)
 
     def __getattr__(self, name: str) -> Any:  # reset / step / rollout / policy_actions / observe ...
         return getattr(self.env, name)

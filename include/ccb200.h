@@ -216,11 +216,17 @@ int cc_rollout_host(cc_handle *h, const cc_step_io *io, int32_t n_steps);
 /* Envs per chunk of the host pipeline (0 = automatic: about N/8, a multiple of 32). */
 int cc_set_host_chunk(cc_handle *h, int64_t chunk_envs);
 
-/* Row delivery of the host path.  n_threads == 0 (default): CC_OBS_INT8 / CC_OBS_FP32 rows are written by the
- * kernel and cross PCIe as they are.  n_threads != 0: the kernel writes the compact table, the table crosses
- * PCIe (4A bytes per env instead of s_obs*A*(6+4A)) and cc_expand_obs_host rebuilds the rows in the caller's
- * buffer on n_threads host threads (< 0: all hardware threads), chunk by chunk while later chunks are still
- * on the device.  The bytes that arrive are identical either way. */
+/* Row delivery of the host path (CC_OBS_INT8 / CC_OBS_FP32 rows requested in host memory).
+ *   n_threads == CC_HOST_EXPAND_OFF (0): the kernel writes the rows and they cross PCIe as they are.
+ *   n_threads  > 0 or CC_HOST_EXPAND_ALL (-1): the kernel writes the compact table, the table crosses PCIe
+ *       (4A bytes per env instead of s_obs*A*(6+4A)) and the rows are rebuilt in the caller's buffer on n_threads
+ *       host threads (ALL: every hardware thread), chunk by chunk while later chunks are still on the device.
+ *   CC_HOST_EXPAND_AUTO (-2, the state of a new handle): as ALL for CC_OBS_FP32 rows when the host has at least 8
+ *       hardware threads and the rows of one call are at least 16 MiB (one B200's PCIe link delivers ~54 GB/s;
+ *       eight threads of non-temporal stores pass that, sixteen reach ~150 GB/s), as OFF otherwise (CC_OBS_INT8
+ *       rows are a quarter of the bytes and cost the host as many instructions: PCIe stays ahead).
+ * The bytes that arrive are identical either way (cc_expand_obs_host is the same code, callable on its own). */
+enum { CC_HOST_EXPAND_OFF = 0, CC_HOST_EXPAND_ALL = -1, CC_HOST_EXPAND_AUTO = -2 };
 int cc_set_host_expand(cc_handle *h, int32_t n_threads);
 
 /* Make the next *_host call wait for everything enqueued on `stream` so far (for work the library cannot see:
@@ -304,6 +310,11 @@ int32_t cc_last_kernel_variant(const cc_handle *h); /* mapping of the last cc_st
 /* instantiation the last step launch ran, e.g. "ccb::cc_step_tpe_kernel<8,4>" (float32 rows), "ccb::cc_step_tpe2_kernel<8,1>"
  * (the small-lattice kernel of the compact modes) or "ccb::cc_kernel<32,2,1,step>"; "" before the first launch */
 const char *cc_last_kernel_name(const cc_handle *h);
+
+/* What the last cc_step_host / cc_rollout_host call did: out[0] chunks, out[1] envs per chunk, out[2] host threads that
+ * rebuilt observation rows (0: the rows crossed PCIe as the kernel wrote them), out[3] bytes copied host -> device,
+ * out[4] bytes copied device -> host (counted from the copies the call enqueued). */
+int cc_last_host_call(const cc_handle *h, int64_t out[5]);
 /* average device time (ms) of the step kernel launches bracketed by cc_timing_begin/_end,
  * measured with CUDA events on the launching stream */
 int cc_timing_begin(cc_handle *h, void *stream);

@@ -145,16 +145,19 @@ def test_step_host_other_crews_with_dict_order(case, obs):
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("expand_threads", [0, 3])
+@pytest.mark.parametrize("expand_threads", [0, 3, -1, -2, None])
 @pytest.mark.parametrize("obs", ["float32", "int8"])
 def test_host_expansion_delivers_the_same_rows(obs, expand_threads):
     """cc_set_host_expand: the table crosses PCIe and the rows are rebuilt in the caller's buffer — same bytes as the
-    rows the kernel writes."""
+    rows the kernel writes.  (-1: all host threads; -2 / None: the automatic choice of a new handle.)"""
     cfg = readme_config(max_steps=20)
     n = 40_000
     a = make_env(cfg, n, seed=8, obs_dtype=obs)
     b = make_env(cfg, n, seed=8, obs_dtype=obs)
-    b.set_host_expand(expand_threads)
+    if expand_threads is not None:
+        b.set_host_expand(expand_threads)
+    with pytest.raises(ValueError, match="cc_set_host_expand"):
+        b.set_host_expand(-3)
     b.set_host_chunk(8192)
     a.reset(); b.reset()
     host = b.make_host_buffers()
