@@ -534,7 +534,8 @@ def run_ours(args):
            "d2h_bytes_per_step": call["d2h_bytes"] + n * A, "steps": args.e2e_steps, "ms_per_step": e2e_ms,
            "host_rows_bytes_per_step": rows_bytes, "expand_threads": call["expand_threads"], "chunks": call["chunks"],
            "path": "cc_policy_actions -> D2H actions (pinned) -> cc_step_host(H2D actions | fused step kernel | D2H "
-                   + ("observation TABLE/reward/flags | float32 rows rebuilt in the caller's buffer by %d host threads (cc_set_host_expand, automatic)" % call["expand_threads"]
+                   + ("observation TABLE/reward/flags | float32 rows rebuilt in the caller's buffer by %d host threads (cc_set_host_expand: %s)"
+                      % (call["expand_threads"], "this rank's share of the node's threads" if world > 1 else "the handle's automatic choice")
                       if call["expand_threads"] else "obs rows/reward/flags")
                    + ", chunks of envs pipelined over three streams); the caller receives the reference's float32 rows"}
     launches_e2e = env.launch_count - launches_before_e2e
