@@ -109,6 +109,7 @@ class BatchedCollectiveCrossing:
         self.seed = int(seed)
         self.global_env_offset = int(global_env_offset)
         self.auto_reset = bool(auto_reset)
+        self.obs_dtype = obs_dtype
         self.obs_torch_dtype, self.obs_code = _OBS_TORCH[obs_dtype]
         self.reward_torch_dtype, self.reward_code = _REW_TORCH[reward_dtype]
 

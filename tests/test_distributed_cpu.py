@@ -92,3 +92,18 @@ def test_reduce_stats_without_process_group_is_identity():
     assert reduce_stats(st) == st
     d = derived_stats(st)
     assert d["episode_len_mean"] == 20 and d["episode_return_mean"] == -1.75 and d["terminated_fraction"] == 0.5
+
+
+def test_host_threads_are_shared_between_the_ranks_of_a_node(monkeypatch):
+    """Ranks of one node split the node's host threads for the host-buffer path (cc_set_host_expand); a lone process keeps the
+    library's automatic choice."""
+    import os
+
+    from collectivecrossing_b200.distributed import host_threads_per_rank
+
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    assert host_threads_per_rank() == 0
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert host_threads_per_rank() == 0
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert host_threads_per_rank() == max(2, (os.cpu_count() or 1) // 8)
