@@ -312,8 +312,9 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
     bool expand = false;
     int expand_threads = 0;   // 0 = every hardware thread
     if (is_rows(io->obs_dtype) && h->host_expand != CC_HOST_EXPAND_OFF) {
-        if (h->host_expand == CC_HOST_EXPAND_AUTO)   // (int8 rows: 16 threads rebuild ~43 GB/s, PCIe delivers ~54: they keep crossing PCIe)
-            expand = io->obs_dtype == CC_OBS_FP32 && std::thread::hardware_concurrency() >= 8 && (size_t)T * (size_t)N * obs_env_bytes(A, io->obs_dtype) >= ((size_t)16 << 20);
+        if (h->host_expand == CC_HOST_EXPAND_AUTO)
+            expand = cc_expand_beats_pcie(&h->cfg, io->obs_dtype) && std::thread::hardware_concurrency() >= 8 &&
+                     (size_t)T * (size_t)N * obs_env_bytes(A, io->obs_dtype) >= ((size_t)16 << 20);
         else { expand = true; expand_threads = h->host_expand > 0 ? h->host_expand : 0; }
     }
     const int k_obs = expand ? CC_OBS_TABLE : io->obs_dtype;
@@ -420,15 +421,24 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
         h->last_host[2] = crew;
         if (!h->workers) h->workers = new cc_worker_pool();
         std::atomic<int> cuda_err{(int)cudaSuccess};
-        // every thread waits for the chunk's event itself and expands its own slice of the chunk: no hand-over between threads
-        h->workers->run(crew, [&](int w) {
+        // the chunks are cut into slices of 4,096 envs that the threads take in order from one counter (a thread that was held up
+        // does not hold up a chunk); a slice may be rebuilt once its chunk's event has completed
+        constexpr long long kSlice = 4096;
+        const long long slices_per_chunk = (chunk + kSlice - 1) / kSlice, n_slices = slices_per_chunk * n_chunks;
+        std::atomic<long long> next{0};
+        h->workers->run(crew, [&](int) {
             cudaSetDevice(h->device);
-            for (long long c = 0; c < n_chunks; ++c) {
-                const long long first = c * chunk, cnt = (N - first < chunk) ? N - first : chunk;
-                const cudaError_t e = cudaEventSynchronize(h->ev_chunk[c]);
-                if (e != cudaSuccess) { cuda_err.store((int)e); return; }
-                const long long per = (cnt + crew - 1) / crew;
-                const long long a = std::min<long long>(cnt, (long long)w * per), b = std::min<long long>(cnt, (long long)(w + 1) * per);
+            long long synced = -1;   // chunks up to here are known to have arrived
+            for (;;) {
+                const long long idx = next.fetch_add(1, std::memory_order_relaxed);
+                if (idx >= n_slices) return;
+                const long long c = idx / slices_per_chunk, first = c * chunk, cnt = (N - first < chunk) ? N - first : chunk;
+                if (c > synced) {
+                    const cudaError_t e = cudaEventSynchronize(h->ev_chunk[c]);
+                    if (e != cudaSuccess) { cuda_err.store((int)e); return; }
+                    synced = c;   // (the events complete in order: one stream)
+                }
+                const long long a = (idx % slices_per_chunk) * kSlice, b = std::min<long long>(cnt, a + kSlice);
                 for (int t = 0; t < T; ++t) {
                     const size_t e0 = (size_t)t * N + (size_t)first;
                     cc_expand_rows_range(&h->cfg, a, b, static_cast<const int8_t *>(h->host_table) + e0 * obs_b,

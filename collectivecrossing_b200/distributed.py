@@ -103,9 +103,10 @@ class ShardedCollectiveCrossing:
         self.device = device
         self.env = env_factory(config, self.count, global_env_offset=self.offset, seed=seed, **env_kwargs)
         self.host_threads = host_threads_per_rank()
-        if self.host_threads and hasattr(self.env, "set_host_expand") and getattr(self.env, "obs_dtype", None) == "float32":
-            # the ranks of a node share its cores AND its PCIe / memory paths: each rebuilds its float32 rows with its share of the
-            # threads (int8 rows keep crossing PCIe, as on a single GPU)
+        od = getattr(self.env, "obs_dtype", None)
+        if self.host_threads and hasattr(self.env, "set_host_expand") and (od == "float32" or (od == "int8" and self.env.num_agents == 8)):
+            # the ranks of a node share its cores AND its PCIe / memory paths: each rebuilds its rows with its share of the threads
+            # (the formats for which the library's automatic choice does so on a single GPU)
             self.env.set_host_expand(self.host_threads)
 
     def __getattr__(self, name: str) -> Any:  # reset / step / rollout / policy_actions / observe ...
