@@ -313,7 +313,7 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
     int expand_threads = 0;   // 0 = every hardware thread
     if (is_rows(io->obs_dtype) && h->host_expand != CC_HOST_EXPAND_OFF) {
         if (h->host_expand == CC_HOST_EXPAND_AUTO)
-            expand = cc_expand_beats_pcie(&h->cfg, io->obs_dtype) && std::thread::hardware_concurrency() >= 8 &&
+            expand = cc_expand_beats_pcie(&h->cfg, io->obs_dtype) && cc_host_threads() >= 8 &&
                      (size_t)T * (size_t)N * obs_env_bytes(A, io->obs_dtype) >= ((size_t)16 << 20);
         else { expand = true; expand_threads = h->host_expand > 0 ? h->host_expand : 0; }
     }

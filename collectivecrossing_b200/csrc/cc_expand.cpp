@@ -19,6 +19,9 @@
 #include <algorithm>
 #include <thread>
 #include <vector>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 #include "../../include/ccb200.h"
 
@@ -211,9 +214,20 @@ bool cc_expand_beats_pcie(const cc_config *cfg, int32_t obs_dtype) {
 #endif
 }
 
-// How many threads a job of n_envs gets when the caller asked for `requested` (<= 0: all the host has).
+// Hardware threads this process may run on (the affinity mask where the OS has one: a rank bound to its GPU's NUMA node, a
+// container pinned to a few cores), not the machine's total.
+int cc_host_threads(void) {
+#if defined(__linux__)
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) return CPU_COUNT(&set);
+#endif
+    const unsigned n = std::thread::hardware_concurrency();
+    return n ? (int)n : 1;
+}
+
+// How many threads a job of n_envs gets when the caller asked for `requested` (<= 0: all this process may use).
 int cc_expand_thread_count(int32_t requested, int64_t n_envs) {
-    int threads = requested > 0 ? requested : (int)std::thread::hardware_concurrency();
+    int threads = requested > 0 ? requested : cc_host_threads();
     if (threads < 1) threads = 1;
     const int64_t min_per_thread = 2048;   // below this a thread's start-up costs more than its share
     return (int)std::max<int64_t>(1, std::min<int64_t>(threads, (n_envs + min_per_thread - 1) / min_per_thread));

@@ -78,6 +78,7 @@ struct cc_handle {
 
 // cc_expand.cpp: rows of envs [e0, e1) of `table` into `obs` on the calling thread; threads a job of n_envs is worth
 void cc_expand_rows_range(const cc_config *cfg, int64_t e0, int64_t e1, const int8_t *table, void *obs, int32_t obs_dtype);
+int cc_host_threads(void);
 int cc_expand_thread_count(int32_t requested, int64_t n_envs);
 bool cc_expand_beats_pcie(const cc_config *cfg, int32_t obs_dtype);
 

@@ -220,8 +220,8 @@ int cc_set_host_chunk(cc_handle *h, int64_t chunk_envs);
  *   n_threads == CC_HOST_EXPAND_OFF (0): the kernel writes the rows and they cross PCIe as they are.
  *   n_threads  > 0 or CC_HOST_EXPAND_ALL (-1): the kernel writes the compact table, the table crosses PCIe
  *       (4A bytes per env instead of s_obs*A*(6+4A)) and the rows are rebuilt in the caller's buffer on n_threads
- *       host threads (ALL: every hardware thread), chunk by chunk while later chunks are still on the device.
- *   CC_HOST_EXPAND_AUTO (-2, the state of a new handle): as ALL when the host has at least 8 hardware threads, the rows
+ *       host threads (ALL: every hardware thread the process may run on), chunk by chunk while later chunks are still on the device.
+ *   CC_HOST_EXPAND_AUTO (-2, the state of a new handle): as ALL when the process may run on at least 8 hardware threads, the rows
  *       of one call are at least 16 MiB and rebuilding beats the link — CC_OBS_FP32 rows always (one B200's PCIe link
  *       delivers ~54 GB/s; a thread streams ~10 GB/s of float32 rows, sixteen reach the host's DRAM write rate), CC_OBS_INT8
  *       rows for crews of 8 on x86-64 with SSSE3 (a byte-shuffle path, 27 GB/s per thread; other crews: 4 GB/s per thread,

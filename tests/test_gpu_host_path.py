@@ -170,7 +170,7 @@ def test_host_expansion_delivers_the_same_rows(obs, expand_threads):
     assert call["chunks"] == -(-n // 8192) and call["chunk_envs"] == 8192 and call["h2d_bytes"] == 0     # the policy runs in the kernel
     if expand_threads in (None, -2):   # the automatic choice: float32 rows of >= 16 MiB on a host with >= 8 threads
         import os
-        assert (call["expand_threads"] > 0) == ((os.cpu_count() or 1) >= 8 and rows >= 16 << 20)   # (crew of 8: int8 rows qualify too)
+        assert (call["expand_threads"] > 0) == (len(os.sched_getaffinity(0)) >= 8 and rows >= 16 << 20)   # (crew of 8: int8 rows qualify too)
     else:
         assert (call["expand_threads"] > 0) == (expand_threads != 0)
     per_env = (4 * 8 if call["expand_threads"] else rows // n) + 4 * 8 + 8 + 8 + 1     # table or rows, rewards, flags, actions, env flags
