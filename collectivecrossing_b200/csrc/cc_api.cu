@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <utility>
@@ -300,6 +301,24 @@ int copy_slices(void *dst, const void *src, size_t row_bytes, int T, long long c
     return CC_OK;
 }
 
+// ordinary (malloc / numpy) memory: copies to and from it are staged by the driver inside the calling thread
+bool is_pageable(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int grow_pinned(void **block, size_t *have, size_t need, const char *what) {
+    if (need <= *have) return CC_OK;
+    if (*block) CC_CUDA(cudaFreeHost(*block));
+    *block = nullptr; *have = 0;
+    cudaError_t e = cudaHostAlloc(block, need, cudaHostAllocDefault);
+    if (e != cudaSuccess) return cc_fail(CC_ERR_NOMEM, "cudaHostAlloc(%zu) for %s: %s", need, what, cudaGetErrorString(e));
+    *have = need;
+    return CC_OK;
+}
+
 int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
     int rc = check_io(h, io);
     if (rc != CC_OK) return rc;
@@ -341,19 +360,68 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
     rc = ensure_host_path(h, set_bytes * ring);
     if (rc != CC_OK) return rc;
     if (expand) {
-        const size_t need = (size_t)T * N * obs_b;
-        if (need > h->host_table_bytes) {
-            if (h->host_table) CC_CUDA(cudaFreeHost(h->host_table));
-            h->host_table = nullptr; h->host_table_bytes = 0;
-            cudaError_t e = cudaHostAlloc(&h->host_table, need, cudaHostAllocDefault);
-            if (e != cudaSuccess) return cc_fail(CC_ERR_NOMEM, "cudaHostAlloc(%zu) for the observation tables: %s", need, cudaGetErrorString(e));
-            h->host_table_bytes = need;
+        rc = grow_pinned(&h->host_table, &h->host_table_bytes, (size_t)T * N * obs_b, "the observation tables");
+        if (rc != CC_OK) return rc;
+    }
+    // Pageable caller buffers (malloc, numpy): a copy to or from them is staged by the driver inside the calling thread (~15 GB/s and
+    // the pipeline stands still meanwhile).  With host threads at hand such arrays go through pinned mirrors [T][N] of the handle:
+    // the copies run at link speed and the threads move the bytes between mirror and caller, slice by slice.
+    struct Mirror { char *user, *pinned; size_t row_b; };
+    Mirror mir[6];
+    int n_mir = 0;
+    char *act_src = const_cast<char *>(reinterpret_cast<const char *>(io->actions));   // where the H2D copies of the actions read
+    const bool crew_ok = h->host_expand > 0 || h->host_expand == CC_HOST_EXPAND_ALL || (h->host_expand == CC_HOST_EXPAND_AUTO && cc_host_threads() >= 8);
+    {
+        struct Out { void *p; size_t row_b; };
+        const Out outs[6] = {{expand ? nullptr : io->obs, obs_b}, {io->reward, rew_b}, {io->agent_flags, (size_t)A}, {io->agent_info, (size_t)A},
+                             {io->actions_out, (size_t)A}, {io->env_flags, 1}};
+        size_t total = 0, mirrored = 0;
+        for (const Out &o : outs) total += o.p ? (size_t)T * N * o.row_b : 0;
+        if (crew_ok && total >= ((size_t)4 << 20)) {
+            size_t moff = 0;
+            for (const Out &o : outs) {
+                const size_t bytes = (size_t)T * N * o.row_b;
+                if (!o.p || !bytes || bytes > ((size_t)512 << 20) || !is_pageable(o.p)) continue;   // (huge arrays: no second copy of them)
+                mir[n_mir++] = Mirror{static_cast<char *>(o.p), reinterpret_cast<char *>(moff), o.row_b};
+                moff = align256(moff + bytes);
+            }
+            size_t act_off = 0;
+            const bool mirror_actions = io->actions && (size_t)T * N * A >= ((size_t)1 << 20) && is_pageable(io->actions);
+            if (mirror_actions) { act_off = moff; moff = align256(moff + (size_t)T * N * A); }
+            mirrored = moff;
+            if (mirrored) {
+                rc = grow_pinned(&h->host_mirror, &h->host_mirror_bytes, mirrored, "the mirrors of pageable buffers");
+                if (rc != CC_OK) return rc;
+                for (int k = 0; k < n_mir; ++k) mir[k].pinned = static_cast<char *>(h->host_mirror) + reinterpret_cast<size_t>(mir[k].pinned);
+                if (mirror_actions) act_src = static_cast<char *>(h->host_mirror) + act_off;
+            }
         }
-        while ((long long)h->ev_chunk.size() < n_chunks) {
-            cudaEvent_t ev;
-            CC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            h->ev_chunk.push_back(ev);
-        }
+    }
+    auto dst_of = [&](void *user) -> void * {   // where the D2H copies of this output land
+        for (int k = 0; k < n_mir; ++k)
+            if (mir[k].user == user) return mir[k].pinned;
+        return user;
+    };
+    const int crew = (expand || n_mir || act_src != reinterpret_cast<const char *>(io->actions)) ? cc_expand_thread_count(expand_threads, chunk) : 1;
+    if (crew > 1 && !h->workers) h->workers = new cc_worker_pool();
+    auto run_crew = [&](const std::function<void(int)> &fn) {
+        if (crew > 1) h->workers->run(crew, fn);
+        else fn(0);
+    };
+    if (expand || n_mir) {
+        for (std::vector<cudaEvent_t> *evs : {&h->ev_chunk, &h->ev_done})
+            while ((long long)evs->size() < n_chunks) {
+                cudaEvent_t ev;
+                CC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                evs->push_back(ev);
+            }
+    }
+    if (act_src != reinterpret_cast<const char *>(io->actions)) {   // the caller's actions into the pinned mirror, all threads at once
+        const size_t bytes = (size_t)T * N * A, per = (bytes / crew + 4095) & ~(size_t)4095;
+        run_crew([&](int w) {
+            const size_t a = std::min(bytes, (size_t)w * per), b = std::min(bytes, (size_t)(w + 1) * per);
+            if (a < b) memcpy(act_src + a, reinterpret_cast<const char *>(io->actions) + a, b - a);
+        });
     }
     if (h->order_pending) {   // everything enqueued on the caller's streams so far happens before this call
         CC_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_order, 0));
@@ -384,7 +452,7 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
         const bool reuse = c >= ring;
         if (io->actions || io->order) {
             if (reuse) CC_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_k[set], 0));   // the kernel that read this set's actions is done
-            if (io->actions) { rc = copy_slices(b + o_act, io->actions, A, T, cnt, N, first, true, h->s_in); if (rc != CC_OK) return rc; }
+            if (io->actions) { rc = copy_slices(b + o_act, act_src, A, T, cnt, N, first, true, h->s_in); if (rc != CC_OK) return rc; }
             if (io->order) { rc = copy_slices(b + o_ord, io->order, A, 1, cnt, N, first, true, h->s_in); if (rc != CC_OK) return rc; }
             CC_CUDA(cudaEventRecord(h->ev_in[set], h->s_in));
             CC_CUDA(cudaStreamWaitEvent(h->s_k, h->ev_in[set], 0));
@@ -396,16 +464,17 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
         CC_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_k[set], 0));
         // the biggest output first, the per-env flags last
         if (obs_b) {
-            rc = copy_slices(expand ? h->host_table : io->obs, d.obs, obs_b, T, cnt, N, first, false, h->s_out);
+            rc = copy_slices(expand ? h->host_table : dst_of(io->obs), d.obs, obs_b, T, cnt, N, first, false, h->s_out);
             if (rc != CC_OK) return rc;
             if (expand) CC_CUDA(cudaEventRecord(h->ev_chunk[c], h->s_out));
         }
-        rc = copy_slices(io->reward, d.reward, rew_b, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc;
-        rc = copy_slices(io->agent_flags, d.agent_flags, A, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc;
-        if (io->agent_info) { rc = copy_slices(io->agent_info, d.agent_info, A, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc; }
-        if (io->actions_out) { rc = copy_slices(io->actions_out, d.actions_out, A, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc; }
-        rc = copy_slices(io->env_flags, d.env_flags, 1, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc;
+        rc = copy_slices(dst_of(io->reward), d.reward, rew_b, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc;
+        rc = copy_slices(dst_of(io->agent_flags), d.agent_flags, A, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc;
+        if (io->agent_info) { rc = copy_slices(dst_of(io->agent_info), d.agent_info, A, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc; }
+        if (io->actions_out) { rc = copy_slices(dst_of(io->actions_out), d.actions_out, A, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc; }
+        rc = copy_slices(dst_of(io->env_flags), d.env_flags, 1, T, cnt, N, first, false, h->s_out); if (rc != CC_OK) return rc;
         CC_CUDA(cudaEventRecord(h->ev_out[set], h->s_out));
+        if (n_mir) CC_CUDA(cudaEventRecord(h->ev_done[c], h->s_out));
     }
     return CC_OK;
     };
@@ -415,34 +484,42 @@ int host_pipeline(cc_handle *h, const cc_step_io *io, int T) {
         return rc;
     }
     h->t = t0 + (uint64_t)T;
-    if (expand) {   // rebuild the rows of every chunk as soon as its table has arrived (later chunks are still in flight)
+    if (expand || n_mir) {
+        // The chunks are cut into slices of 4,096 envs that the threads take in order from one counter (a thread that was held up
+        // does not hold up a chunk).  Pass 1: the rows of a slice are rebuilt once the chunk's table has arrived (later chunks are
+        // still in flight); pass 2: the mirrored outputs of a slice are copied out once all of the chunk's copies have completed.
         const size_t row_b = obs_env_bytes(A, io->obs_dtype);
-        const int crew = cc_expand_thread_count(expand_threads, chunk);
-        h->last_host[2] = crew;
-        if (!h->workers) h->workers = new cc_worker_pool();
+        h->last_host[2] = expand ? crew : 0;
         std::atomic<int> cuda_err{(int)cudaSuccess};
-        // the chunks are cut into slices of 4,096 envs that the threads take in order from one counter (a thread that was held up
-        // does not hold up a chunk); a slice may be rebuilt once its chunk's event has completed
         constexpr long long kSlice = 4096;
         const long long slices_per_chunk = (chunk + kSlice - 1) / kSlice, n_slices = slices_per_chunk * n_chunks;
-        std::atomic<long long> next{0};
-        h->workers->run(crew, [&](int) {
+        std::atomic<long long> next_rows{0}, next_out{0};
+        run_crew([&](int) {
             cudaSetDevice(h->device);
-            long long synced = -1;   // chunks up to here are known to have arrived
-            for (;;) {
-                const long long idx = next.fetch_add(1, std::memory_order_relaxed);
-                if (idx >= n_slices) return;
-                const long long c = idx / slices_per_chunk, first = c * chunk, cnt = (N - first < chunk) ? N - first : chunk;
-                if (c > synced) {
-                    const cudaError_t e = cudaEventSynchronize(h->ev_chunk[c]);
-                    if (e != cudaSuccess) { cuda_err.store((int)e); return; }
-                    synced = c;   // (the events complete in order: one stream)
-                }
-                const long long a = (idx % slices_per_chunk) * kSlice, b = std::min<long long>(cnt, a + kSlice);
-                for (int t = 0; t < T; ++t) {
-                    const size_t e0 = (size_t)t * N + (size_t)first;
-                    cc_expand_rows_range(&h->cfg, a, b, static_cast<const int8_t *>(h->host_table) + e0 * obs_b,
-                                         static_cast<char *>(io->obs) + e0 * row_b, io->obs_dtype);
+            for (int pass = expand ? 0 : 1; pass < (n_mir ? 2 : 1); ++pass) {
+                std::atomic<long long> &next = pass == 0 ? next_rows : next_out;
+                const std::vector<cudaEvent_t> &evs = pass == 0 ? h->ev_chunk : h->ev_done;
+                long long synced = -1;   // chunks up to here are known to have arrived (the events complete in order: one stream)
+                for (;;) {
+                    const long long idx = next.fetch_add(1, std::memory_order_relaxed);
+                    if (idx >= n_slices) break;
+                    const long long c = idx / slices_per_chunk, first = c * chunk, cnt = (N - first < chunk) ? N - first : chunk;
+                    if (c > synced) {
+                        const cudaError_t e = cudaEventSynchronize(evs[c]);
+                        if (e != cudaSuccess) { cuda_err.store((int)e); return; }
+                        synced = c;
+                    }
+                    const long long a = (idx % slices_per_chunk) * kSlice, b = std::min<long long>(cnt, a + kSlice);
+                    if (a >= b) continue;
+                    for (int t = 0; t < T; ++t) {
+                        const size_t e0 = (size_t)t * N + (size_t)first;
+                        if (pass == 0)
+                            cc_expand_rows_range(&h->cfg, a, b, static_cast<const int8_t *>(h->host_table) + e0 * obs_b,
+                                                 static_cast<char *>(io->obs) + e0 * row_b, io->obs_dtype);
+                        else
+                            for (int k = 0; k < n_mir; ++k)
+                                memcpy(mir[k].user + (e0 + (size_t)a) * mir[k].row_b, mir[k].pinned + (e0 + (size_t)a) * mir[k].row_b, (size_t)(b - a) * mir[k].row_b);
+                    }
                 }
             }
         });
@@ -535,6 +612,8 @@ void cc_destroy(cc_handle *h) {
     if (h->stage_block) cudaFree(h->stage_block);
     delete h->workers;
     if (h->host_table) cudaFreeHost(h->host_table);
+    if (h->host_mirror) cudaFreeHost(h->host_mirror);
+    for (cudaEvent_t ev : h->ev_done) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_chunk) cudaEventDestroy(ev);
     if (h->gen) cudaFree(h->gen);
     if (h->t2_tables) cudaFree(h->t2_tables);

@@ -70,7 +70,10 @@ struct cc_handle {
     int host_expand = CC_HOST_EXPAND_AUTO;   // cc_set_host_expand: threads that rebuild observation rows on the host (0 = rows cross PCIe)
     void *host_table = nullptr;          // pinned scratch of the tables the host expands
     size_t host_table_bytes = 0;
-    std::vector<cudaEvent_t> ev_chunk;   // one event per chunk: its outputs are complete in host memory
+    void *host_mirror = nullptr;         // pinned mirrors of the caller's pageable buffers
+    size_t host_mirror_bytes = 0;
+    std::vector<cudaEvent_t> ev_chunk;   // one event per chunk: its observation table is complete in host memory
+    std::vector<cudaEvent_t> ev_done;    // one event per chunk: all its outputs are complete in host memory
     int64_t last_host[5] = {};           // cc_last_host_call: chunks, envs per chunk, expanding threads, H2D bytes, D2H bytes
     cc_worker_pool *workers = nullptr;   // the threads that expand (created by the first call that needs them)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // cc_timing_*

@@ -200,7 +200,10 @@ int cc_get_state_host(cc_handle *h, int8_t *x, int8_t *y, uint8_t *flags, int32_
  * handle in ONE fused kernel launch on `stream` (a cudaStream_t; NULL = legacy default). */
 int cc_step(cc_handle *h, const cc_step_io *io, void *stream);
 
-/* Same with every pointer of `io` a HOST pointer (pinned for full PCIe speed, pageable works).
+/* Same with every pointer of `io` a HOST pointer.  Pinned buffers are copied to and from directly; ordinary (malloc / numpy)
+ * buffers go through pinned mirrors owned by the handle, filled at link speed and moved to / from the caller's memory by the
+ * handle's host threads (a direct copy to pageable memory is staged by the driver inside the calling thread: 3x slower for
+ * the compact formats) — unless cc_set_host_expand(h, 0) leaves the handle without host threads.
  * This is the call a non-CUDA caller (numpy, the reference's RLlib env-runner) binds.  The envs
  * are processed in chunks on three streams of the handle — chunk c+1's host->device copy of
  * the actions and its kernel overlap chunk c's device->host copies of the outputs — and the call

@@ -289,3 +289,34 @@ def test_auto_reset_attempt_cap_is_the_same_in_both_mappings():
         with pytest.raises(Exception, match="no free valid cell"):
             env.check_error()
         env.close()
+
+
+@pytest.mark.parametrize("obs,expand", [("float32", -2), ("table", -2), ("int8", 0), ("float32", 0)])
+def test_pageable_buffers_go_through_pinned_mirrors_with_the_same_bytes(obs, expand):
+    """Host buffers in ordinary (numpy / malloc) memory: the outputs land in pinned mirrors of the handle and its host threads copy
+    them out, the actions are gathered into a mirror first — the bytes the caller sees are those of the device step."""
+    cfg = readme_config(max_steps=25)
+    n = 150_000
+    a = make_env(cfg, n, seed=4, obs_dtype=obs, with_info=True)
+    b = make_env(cfg, n, seed=4, obs_dtype=obs, with_info=True)
+    b.set_host_expand(expand)
+    a.reset(); b.reset()
+    host = b.make_host_buffers(pinned=False)
+    assert not host["reward"].is_pinned()
+    for t in range(8):
+        acts = a.policy_actions("greedy" if t % 2 else "waiting").clone()
+        out = a.step(acts)
+        host["actions"].copy_(acts)
+        b.step_host(host)
+        assert torch.equal(out.obs.cpu(), host["obs"]) and torch.equal(out.reward.cpu(), host["reward"]), t
+        assert torch.equal(out.agent_flags.cpu(), host["agent_flags"]) and torch.equal(out.env_flags.cpu(), host["env_flags"]), t
+        assert torch.equal(out.agent_info.cpu(), host["agent_info"]) and torch.equal(acts.cpu(), host["actions_out"]), t
+    T = 3
+    hostT = b.make_host_buffers(pinned=False, n_steps=T)
+    traj = a.rollout_trajectory(T, policy="waiting")
+    b.rollout_host(hostT, T, policy="waiting")
+    for k in ("obs", "reward", "agent_flags", "agent_info", "env_flags"):
+        assert torch.equal(traj[k].cpu(), hostT[k]), k
+    assert torch.equal(traj["actions"].cpu(), hostT["actions_out"])
+    assert torch.equal(a.x, b.x) and torch.equal(a.flags, b.flags)
+    a.close(); b.close()
