@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--steps-per-launch", type=int, default=20,
                     help="env-steps fused into one launch (cc_rollout_fused); 1 = one launch per step")
     ap.add_argument("--reps", type=int, default=5, help="repetitions of the timed region (the median is reported)")
-    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
