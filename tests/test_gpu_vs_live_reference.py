@@ -11,7 +11,7 @@ import multiprocessing as mp
 
 import numpy as np
 import pytest
-from cases import readme_config
+from cases import large_config, readme_config
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -20,19 +20,50 @@ torch = pytest.importorskip("torch")
 def _record_chunk(job):
     from oracle import refrun
 
-    kind, seeds, n_steps = job
-    return refrun.record(readme_config(), seeds, n_steps, source=kind)
+    make_cfg, kind, seeds, n_steps, kw = job
+    return refrun.record(_CONFIGS[make_cfg](), seeds, n_steps, source=kind, **kw)
 
 
-def _record_parallel(kind, seeds, n_steps, workers=8):
+_CONFIGS = {
+    "readme": readme_config,
+    "cfg3": lambda: large_config(max_steps=40),                                                  # BASELINE config 3: 64x32, 48 + 16 agents
+    "cfg4_binary": lambda: readme_config(reward="binary", term="individual", max_steps=100),     # BASELINE config 4
+    "cfg4_constant_negative": lambda: readme_config(reward="constant_negative", term="individual", max_steps=100),
+}
+
+
+def _record_parallel(kind, seeds, n_steps, workers=8, make_cfg="readme", **kw):
     chunks = [list(c) for c in np.array_split(np.asarray(seeds), workers) if len(c)]
     with mp.get_context("spawn").Pool(len(chunks)) as pool:
-        parts = pool.map(_record_chunk, [(kind, c, n_steps) for c in chunks])
+        parts = pool.map(_record_chunk, [(make_cfg, kind, c, n_steps, dict(kw, stream_seed=kw.get("stream_seed", 0) + k)) for k, c in enumerate(chunks)])
     out = {}
     for k in parts[0]:
         axis = 0 if k.startswith("init_") else 1
         out[k] = np.concatenate([p[k] for p in parts], axis=axis)
     return out
+
+
+@pytest.mark.parametrize("make_cfg,n_envs,n_steps,obs,kernel", [
+    ("cfg3", 24, 48, "int8", "auto"), ("cfg3", 16, 44, "float32", "auto"),
+    ("cfg4_binary", 96, 108, "float32", "threads"), ("cfg4_constant_negative", 96, 108, "int8", "threads"), ("cfg4_binary", 40, 104, "int8", "lanes")])
+def test_baseline_shapes_against_the_live_reference(make_cfg, n_envs, n_steps, obs, kernel):
+    """BASELINE configs 3 and 4 as shapes: the unmodified reference steps its envs with random action dicts in random order with
+    missing agents, here and now; the device replays the same actions through the kernel each shape runs on.  (Config 4's
+    truncation at MaxSteps 100 falls inside the window; the reference keeps stepping finished envs, so does the replay.)"""
+    from helpers import assert_same, replay_device
+    from oracle import refload
+
+    if not refload.available():
+        pytest.skip("reference neither mounted nor staged")
+    threads = kernel == "threads"   # the thread-per-env kernel: agent order, float32 rewards (the correctly rounded float64)
+    rec = _record_parallel("random", list(range(300, 300 + n_envs)), n_steps, make_cfg=make_cfg, validate=False, shuffle_order=not threads,
+                           drop_prob=0.0 if threads else 0.1, stream_seed=17)
+    got = replay_device(_CONFIGS[make_cfg](), rec, use_order=not threads, obs_dtype=obs, reward_dtype="float32" if threads else "float64", kernel=kernel)
+    if threads:
+        rec = dict(rec, reward=rec["reward"].astype(np.float32).astype(np.float64))
+        assert got["_kernel"] == "threads"
+    assert_same(rec, got, f"{make_cfg}/{obs}/{kernel}")
+    assert (rec["env_flags"] != 0).any() or make_cfg == "cfg3"
 
 
 @pytest.mark.parametrize("kind,n_steps", [("greedy", 105), ("waiting", 70)])
