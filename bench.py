@@ -461,6 +461,8 @@ def run_ours(args):
     if T > 1:
         n_launch = max(1, -(-args.steps // T))
         T = max(1, args.steps // n_launch)
+    # (the sampling thread starts before the warm-up: NVML's first queries can take longer than a whole timed region)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         env.step(policy=args.policy)
     if T > 1:
@@ -472,7 +474,6 @@ def run_ours(args):
 
     # the timed region (K steps) is repeated; the median repetition is the value, every repetition is reported
     reps = max(1, args.reps)
-    sampler = ClockSampler(local) if rank == 0 else None
     rep_ms, stats_t, launches = [], None, 0
     if sampler:
         sampler.mark_begin()
