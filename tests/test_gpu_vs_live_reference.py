@@ -155,3 +155,43 @@ def test_facade_against_the_live_reference_on_random_configs(seed):
                     assert g[k] == w[k], f"step {t}: {what}[{k}]: {g[k]!r} vs {w[k]!r}"      # floats compare exactly: same float64 arithmetic
         assert ours.agents == theirs.agents or set(ours.agents) == set(theirs.agents)
     ours.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_config1_recipe_with_unseeded_resets_against_the_live_reference(seed):
+    """BASELINE config 1 as SURVEY.md §8d words it (C1): README config, one env, `reset(seed=s)`, actions
+    `np.random.default_rng(s).integers(0, 5, size=A)` per step in agent order, `reset()` — WITHOUT a seed, i.e. continuing the env's
+    generator where the last placement left it — whenever the episode is over.  The façade (every step and every placement on the
+    device) must track the reference through several episodes."""
+    from oracle import refload
+
+    from collectivecrossing_b200 import CollectiveCrossingEnv
+
+    if not refload.available():
+        pytest.skip("reference neither mounted nor staged")
+    ref = refload.load()
+    cfg = readme_config(max_steps=40)
+    ours, theirs = CollectiveCrossingEnv(cfg), ref.CollectiveCrossingEnv(refload.to_reference_config(cfg))
+    o1, i1 = ours.reset(seed=seed)
+    o2, i2 = theirs.reset(seed=seed)
+    assert all(np.array_equal(o1[k], o2[k]) for k in o2) and i1 == i2
+    ids = ours.possible_agents
+    rng = np.random.default_rng(seed)
+    episodes = 0
+    for t in range(260):
+        draw = rng.integers(0, 5, size=len(ids))
+        acts = {a: int(v) for a, v in zip(ids, draw) if a in theirs.agents}
+        r1, r2 = ours.step(dict(acts)), theirs.step(dict(acts))
+        for what, g, w in zip(("observations", "rewards", "terminateds", "truncateds", "infos"), r1, r2):
+            assert set(g) == set(w), f"step {t}: keys of {what}"
+            for k in g:
+                assert np.array_equal(g[k], w[k]) if isinstance(g[k], np.ndarray) else g[k] == w[k], f"step {t}: {what}[{k}]"
+        assert set(ours.agents) == set(theirs.agents)
+        if r2[2]["__all__"] or r2[3]["__all__"]:
+            episodes += 1
+            o1, i1 = ours.reset()
+            o2, i2 = theirs.reset()
+            assert o1.keys() == o2.keys() and all(np.array_equal(o1[k], o2[k]) for k in o2), f"reset() after episode {episodes}: placement"
+            assert i1 == i2
+    assert episodes >= 5
+    ours.close()
