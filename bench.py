@@ -573,6 +573,11 @@ def run_ours(args):
     if not args.no_extras:
         if world == 1:
             extras = secondary(args, torch, dist, cfg)
+            try:   # BASELINE config 5's 1-GPU point: all 16.8 M envs on this GPU
+                torch.cuda.empty_cache()
+                extras.update(config5_sharded(args, torch, dist, cfg, world, rank, dev))
+            except RuntimeError as exc:  # noqa: BLE001 - e.g. not enough free HBM next to another tenant: reported, not fatal
+                extras["cfg5_16M_envs_waiting_sharded"] = {"error": str(exc)[:200]}
         else:
             extras = config5_sharded(args, torch, dist, cfg, world, rank, dev)
 
@@ -605,11 +610,12 @@ def run_ours(args):
 
 def config5_sharded(args, torch, dist, cfg, world, rank, dev):
     """BASELINE config 5 as stated: 16,777,216 README envs sharded over the job's GPUs, waiting policy in the kernel, auto-reset,
-    float32 rows, fused launches of 8 env-steps with ONE NCCL all-reduce of the episode statistics per launch inside the timed
-    region (median of 3 regions of 5 launches)."""
+    float32 rows, fused launches of 8 env-steps (2 on a single GPU) with ONE NCCL all-reduce of the episode statistics per launch
+    inside the timed region at N > 1 (median of 3 regions of 5 launches; 10 on a single GPU)."""
     from collectivecrossing_b200.distributed import ShardedCollectiveCrossing
 
-    total, T, launches = 1 << 24, 8, 5
+    # (on ONE GPU the [T, 16.8 M, 8, 38] float32 rows of a fused launch of 8 would be 163 GB: 2 steps per launch there)
+    total, T, launches = 1 << 24, (8 if world > 1 else 2), (5 if world > 1 else 10)
     sh = ShardedCollectiveCrossing(cfg, total, seed=5, device=dev, obs_dtype="float32", auto_reset=True)
     env = sh.env
     env.reset()
