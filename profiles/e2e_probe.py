@@ -27,12 +27,12 @@ cfg = readme_config()
 dev = torch.device("cuda:0")
 
 
-def run(tag, obs, chunk=0, expand=0, policy_on_device=False, T=1):
+def run(tag, obs, chunk=0, expand=0, policy_on_device=False, T=1, pinned=True):
     env = BatchedCollectiveCrossing(cfg, n, dev, seed=1, obs_dtype=obs if obs else "none", auto_reset=True)
     env.set_host_chunk(chunk)
     env.set_host_expand(expand)
     env.reset()
-    host = env.make_host_buffers(pinned=True, n_steps=None if T == 1 else T)
+    host = env.make_host_buffers(pinned=pinned, n_steps=None if T == 1 else T)
     dev_actions = torch.zeros((n, A), dtype=torch.int8, device=dev)
 
     def step():
@@ -53,28 +53,35 @@ def run(tag, obs, chunk=0, expand=0, policy_on_device=False, T=1):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / (args.steps * T)
-    obs_b = 0 if host["obs"] is None else host["obs"].numel() * host["obs"].element_size() // T
-    if expand:
-        obs_b = n * A * 4
-    d2h = obs_b + n * A * 4 + 3 * n * A + n + (0 if policy_on_device or T > 1 else n * A)
-    print(json.dumps({"tag": tag, "obs": obs, "chunk": chunk, "expand_threads": expand, "steps_per_call": T, "ms_per_step": round(dt * 1e3, 3),
-                      "agent_steps_per_sec": round(n * A / dt), "d2h_bytes_per_step": d2h, "pcie_GBps": round(d2h / dt / 1e9, 1)}), flush=True)
+    call = env.last_host_call()
+    d2h = call["d2h_bytes"] // T + (0 if policy_on_device or T > 1 else n * A)
+    print(json.dumps({"tag": tag, "obs": obs, "pinned": pinned, "chunks": call["chunks"], "expand_threads": call["expand_threads"], "steps_per_call": T,
+                      "ms_per_step": round(dt * 1e3, 3), "agent_steps_per_sec": round(n * A / dt), "d2h_bytes_per_step": d2h,
+                      "pcie_GBps": round(d2h / dt / 1e9, 1)}), flush=True)
     env.close()
     del env, host
     torch.cuda.empty_cache()
 
 
+AUTO = -2
+run("fp32 rows, the handle's own delivery (table over PCIe, rows rebuilt by the host threads)", "float32", expand=AUTO)
 run("fp32 rows over PCIe", "float32")
 run("fp32 rows over PCIe, one chunk", "float32", chunk=n)
 run("fp32 rows over PCIe, 32 chunks", "float32", chunk=n // 32)
+run("fp32 rows rebuilt on the host, 8 threads", "float32", expand=8)
+run("fp32 rows rebuilt on the host, 4 threads", "float32", expand=4)
+run("fp32 rows rebuilt on the host, 4 chunks", "float32", expand=AUTO, chunk=n // 4)
+run("fp32 rows rebuilt on the host, policy on device", "float32", expand=AUTO, policy_on_device=True)
+run("int8 rows, the handle's own delivery", "int8", expand=AUTO)
 run("int8 rows over PCIe", "int8")
-run("table", "table")
-run("table, one chunk", "table", chunk=n)
-run("table, 4 chunks", "table", chunk=n // 4)
-run("table, policy on device", "table", policy_on_device=True)
-run("no observations", None)
-run("fp32 rows rebuilt on the host (all threads)", "float32", expand=-1)
-run("fp32 rows rebuilt on the host (8 threads)", "float32", expand=8)
-run("int8 rows rebuilt on the host (all threads)", "int8", expand=-1)
-run("rollout_host T=8 fp32", "float32", T=8)
-run("rollout_host T=8 table", "table", T=8)
+run("table", "table", expand=AUTO)
+run("table, one chunk", "table", chunk=n, expand=AUTO)
+run("table, 4 chunks", "table", chunk=n // 4, expand=AUTO)
+run("table, policy on device", "table", policy_on_device=True, expand=AUTO)
+run("no observations", None, expand=AUTO)
+run("rollout_host T=8 fp32", "float32", T=8, expand=AUTO)
+run("rollout_host T=8 table", "table", T=8, expand=AUTO)
+# ordinary (pageable) caller memory: through the handle's pinned mirrors, and with the host threads switched off
+run("fp32 rows, pageable buffers", "float32", expand=AUTO, pinned=False, policy_on_device=True)
+run("table, pageable buffers", "table", expand=AUTO, pinned=False, policy_on_device=True)
+run("table, pageable buffers, no host threads (direct copies)", "table", expand=0, pinned=False, policy_on_device=True)
