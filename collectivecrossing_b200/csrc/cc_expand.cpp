@@ -57,7 +57,10 @@ __attribute__((target("avx2"))) void stream_lines_avx2(unsigned char *dst, const
     }
 }
 using StreamFn = void (*)(unsigned char *, const unsigned char *, size_t);
-StreamFn pick_stream() { return __builtin_cpu_supports("avx2") ? stream_lines_avx2 : stream_lines_sse2; }
+StreamFn pick_stream() {
+    __builtin_cpu_init();   // (a static initialiser of a dlopen'ed library: do not rely on libgcc's own constructor having run)
+    return __builtin_cpu_supports("avx2") ? stream_lines_avx2 : stream_lines_sse2;
+}
 const StreamFn g_stream = pick_stream();
 #endif
 
@@ -173,7 +176,7 @@ __attribute__((target("ssse3"))) void expand_int8_a8_ssse3(const Int8A8Plan &pl,
     }
     _mm_sfence();
 }
-const bool g_ssse3 = __builtin_cpu_supports("ssse3");
+const bool g_ssse3 = (__builtin_cpu_init(), __builtin_cpu_supports("ssse3"));
 #endif
 
 template <typename T>
