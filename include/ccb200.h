@@ -186,6 +186,7 @@ int cc_attach_state(cc_handle *h, int8_t *x, int8_t *y, uint8_t *flags, int32_t 
                     float *episode_return);
 
 /* --- state injection / checkpoint (tests write env._agents[..] directly) --- */
+/* A NULL array is skipped (partial update / partial read-back); cc_set_state* also zeroes the episode returns. */
 int cc_set_state(cc_handle *h, const int8_t *x, const int8_t *y, const uint8_t *flags,
                  const int32_t *step, void *stream);
 int cc_get_state(cc_handle *h, int8_t *x, int8_t *y, uint8_t *flags, int32_t *step, void *stream);
